@@ -1,0 +1,3 @@
+#!/bin/bash
+# first GPU validation run
+python -m pytest tests -x -q -m gpu 2>&1 | tail -40

@@ -1,0 +1,237 @@
+// Stage a1-a3: batched k-nearest-station search (replaces twx/interp/station_select.py:72-192 +
+// twx/utils/util_geo.py:24-40).
+//
+// One CTA per query point.  The whole station table (lat/lon in radians, cos(lat)) is streamed from L2, the
+// haversine "a" term of every station is written to a shared-memory key table (8 B per station), the
+// (k+1)-th smallest key is found with an 8-pass byte-wise radix select over that table, the keys <= that
+// threshold are compacted and sorted with a bitonic network, and only then the k+1 survivors get the
+// asin/sqrt that turns "a" into kilometres.  Ordering is (distance, station index) ascending: the
+// north_star tie-break, i.e. numpy argsort(kind='stable') of the reference's distance vector.
+//
+// Bit-exactness: the "a" term uses the reference's operation order with explicit _rn intrinsics (no FMA
+// contraction).  a -> km is monotone (sqrt is correctly rounded, asin monotone up to its 1-ulp error); the
+// selected set is re-checked in km and re-sorted on (km, index) if asin ever breaks monotonicity.
+#include "twxi_internal.cuh"
+
+namespace twxi {
+
+constexpr int KNN_THREADS = 256;
+constexpr int KNN_SEL = 512;   // capacity of the compacted candidate list (k+1 <= 256 plus boundary ties)
+
+struct KnnArgs {
+    int n;
+    const double* latrad;
+    const double* lonrad;
+    const double* coslat;
+    const double* qlat;
+    const double* qlon;
+    const int32_t* rm_idx;
+    int n_rm;
+    int rm_zero;
+    int k1;
+    int32_t* out_idx;
+    double* out_dist;
+    double* out_wgt;
+    int32_t* status;
+};
+
+__device__ __forceinline__ bool pair_less(unsigned long long ka, int ia, unsigned long long kb, int ib) {
+    return ka < kb || (ka == kb && ia < ib);
+}
+
+// bitonic sort of P (power of two) (key, idx) pairs in shared memory, ascending
+__device__ void bitonic_sort(unsigned long long* key, int* idx, int P) {
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < P; t += KNN_THREADS) {
+                int p = t ^ j;
+                if (p > t) {
+                    bool asc = (t & k) == 0;
+                    unsigned long long ka = key[t], kb = key[p];
+                    int ia = idx[t], ib = idx[p];
+                    bool sw = asc ? pair_less(kb, ib, ka, ia) : pair_less(ka, ia, kb, ib);
+                    if (sw) { key[t] = kb; key[p] = ka; idx[t] = ib; idx[p] = ia; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(KNN_THREADS) knn_kernel(KnnArgs a) {
+    extern __shared__ unsigned long long smem_u64[];
+    unsigned long long* keys = smem_u64;                       // [n]
+    unsigned long long* selkey = keys + a.n;                   // [KNN_SEL]
+    int* selidx = reinterpret_cast<int*>(selkey + KNN_SEL);    // [KNN_SEL]
+    unsigned* hist = reinterpret_cast<unsigned*>(selidx + KNN_SEL);   // [256]
+    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned s_remaining, s_bincount, s_cnt;
+
+    const int q = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int n = a.n;
+    const int k1 = a.k1;
+    if (a.status[q] != TWXI_ST_OK) return;                     // masked cell / earlier failure
+
+    // ---- phase 1: haversine "a" of every station (util_geo.py:27-36) -------------------------------
+    const double lat1rad = __dmul_rn(a.qlat[q], TWX_RAD);
+    const double lon1rad = __dmul_rn(a.qlon[q], TWX_RAD);
+    const double coslat1 = cos(lat1rad);
+    int rm[TWXI_MAX_RM];
+#pragma unroll
+    for (int i = 0; i < TWXI_MAX_RM; ++i) rm[i] = (i < a.n_rm) ? a.rm_idx[(size_t)q * a.n_rm + i] : -1;
+
+    for (int s = tid; s < n; s += KNN_THREADS) {
+        double av = hav_a(lat1rad, lon1rad, coslat1, a.latrad[s], a.lonrad[s], a.coslat[s]);
+        unsigned long long key = (unsigned long long)__double_as_longlong(av);
+        bool removed = (a.rm_zero && av == 0.0);               // station_select.py:97-99 (d == 0 <=> a == 0)
+#pragma unroll
+        for (int i = 0; i < TWXI_MAX_RM; ++i) removed |= (rm[i] == s);   // :101-104
+        if (removed || !(av >= 0.0)) key = ~0ull;
+        keys[s] = key;
+    }
+    if (tid == 0) { s_prefix = 0ull; s_remaining = (unsigned)k1; s_cnt = 0u; }
+    __syncthreads();
+
+    // ---- phase 2: radix select of the k1-th smallest key -----------------------------------------
+    for (int pass = 0; pass < 8; ++pass) {
+        const int shift = 56 - 8 * pass;
+        const unsigned long long mask = pass == 0 ? 0ull : (~0ull << (shift + 8));
+        hist[tid] = 0u;
+        __syncthreads();
+        const unsigned long long prefix = s_prefix;
+        for (int s = tid; s < n; s += KNN_THREADS) {
+            unsigned long long k = keys[s];
+            if ((k & mask) == prefix) atomicAdd(&hist[(unsigned)(k >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid < 32) {
+            unsigned c[8], sum = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { c[i] = hist[tid * 8 + i]; sum += c[i]; }
+            unsigned incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (tid >= o) incl += v;
+            }
+            unsigned excl = incl - sum;
+            unsigned rem = s_remaining;
+            if (excl < rem && rem <= incl) {
+                unsigned r = rem - excl;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (r <= c[i]) {
+                        s_prefix = prefix | ((unsigned long long)(tid * 8 + i) << shift);
+                        s_remaining = r;
+                        s_bincount = c[i];
+                        break;
+                    }
+                    r -= c[i];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const unsigned long long T = s_prefix;
+    if (T == ~0ull) {   // fewer than k1 candidate stations: IndexError at station_select.py:164
+        if (tid == 0) a.status[q] = TWXI_ST_TOO_FEW_STNS;
+        return;
+    }
+    const unsigned count_le = (unsigned)k1 - s_remaining + s_bincount;
+    if (count_le > (unsigned)KNN_SEL) {
+        if (tid == 0) a.status[q] = TWXI_ST_KNN_TIES;
+        return;
+    }
+
+    // ---- phase 3: compact keys <= T, sort by (key, index) -----------------------------------------
+    int P = 32;
+    while (P < (int)count_le) P <<= 1;
+    for (int t = tid; t < P; t += KNN_THREADS) { selkey[t] = ~0ull; selidx[t] = 0x7fffffff; }
+    __syncthreads();
+    for (int s = tid; s < n; s += KNN_THREADS) {
+        unsigned long long k = keys[s];
+        if (k <= T) {
+            unsigned p = atomicAdd(&s_cnt, 1u);
+            selkey[p] = k;
+            selidx[p] = s;
+        }
+    }
+    __syncthreads();
+    bitonic_sort(selkey, selidx, P);
+
+    // ---- phase 4: kilometres for the k1 survivors; verify (km, index) order ---------------------------
+    int bad = 0;
+    if (tid < k1) {
+        double d = hav_km(__longlong_as_double((long long)selkey[tid]));
+        selkey[tid] = (unsigned long long)__double_as_longlong(d);
+    }
+    __syncthreads();
+    if (tid + 1 < k1) bad = !pair_less(selkey[tid], selidx[tid], selkey[tid + 1], selidx[tid + 1]);
+    if (__syncthreads_or(bad)) {
+        int P2 = 32;
+        while (P2 < k1) P2 <<= 1;
+        for (int t = k1 + tid; t < P2; t += KNN_THREADS) { selkey[t] = ~0ull; selidx[t] = 0x7fffffff; }
+        __syncthreads();
+        bitonic_sort(selkey, selidx, P2);
+    }
+    const double dbw = __longlong_as_double((long long)selkey[k1 - 1]);   // station_select.py:164
+    if (tid < k1) {
+        double d = __longlong_as_double((long long)selkey[tid]);
+        size_t o = (size_t)q * k1 + tid;
+        a.out_idx[o] = selidx[tid];
+        a.out_dist[o] = d;
+        if (a.out_wgt) {                                       // bisquare, station_select.py:169
+            double r = d / dbw;
+            double u = __dsub_rn(1.0, __dmul_rn(r, r));
+            a.out_wgt[o] = __dmul_rn(u, u);
+        }
+    }
+}
+
+__global__ void station_trig_kernel(int n, const double* lon, const double* lat, double* lonrad, double* latrad,
+                                    double* coslat) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        double lr = __dmul_rn(lat[i], TWX_RAD);
+        latrad[i] = lr;
+        lonrad[i] = __dmul_rn(lon[i], TWX_RAD);
+        coslat[i] = cos(lr);
+    }
+}
+
+__global__ void dist_table_kernel(int n, const double* lon, const double* lat, double* H) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.y;
+    if (j < n) H[(size_t)i * n + j] = (i == j) ? 0.0 : gcdist_sp(lon[i], lat[i], lon[j], lat[j]);
+}
+
+int launch_station_trig(cudaStream_t s, int n, const double* lon, const double* lat, double* lonrad,
+                        double* latrad, double* coslat) {
+    station_trig_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, lon, lat, lonrad, latrad, coslat);
+    TWXI_LAUNCH_CHECK();
+    return TWXI_OK;
+}
+
+int launch_build_dist_table(cudaStream_t s, int n, const double* lon, const double* lat, double* H) {
+    dim3 grid((n + 255) / 256, n);
+    dist_table_kernel<<<grid, 256, 0, s>>>(n, lon, lat, H);
+    TWXI_LAUNCH_CHECK();
+    return TWXI_OK;
+}
+
+int launch_knn(Ctx& c, int npts, const double* lat, const double* lon, const int32_t* rm_idx, int n_rm,
+               int rm_zero, int k1, int32_t* idx, double* dist, double* wgt, int32_t* status) {
+    if (npts <= 0) return TWXI_OK;
+    KnnArgs a;
+    a.n = c.n; a.latrad = c.st.latrad; a.lonrad = c.st.lonrad; a.coslat = c.st.coslat;
+    a.qlat = lat; a.qlon = lon; a.rm_idx = rm_idx; a.n_rm = rm_idx ? n_rm : 0; a.rm_zero = rm_zero; a.k1 = k1;
+    a.out_idx = idx; a.out_dist = dist; a.out_wgt = wgt; a.status = status;
+    size_t smem = (size_t)c.n * 8 + KNN_SEL * 12 + 256 * 4;
+    TWXI_CUDA(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    knn_kernel<<<npts, KNN_THREADS, smem, c.stream>>>(a);
+    TWXI_LAUNCH_CHECK();
+    return TWXI_OK;
+}
+
+}  // namespace twxi

@@ -1,0 +1,186 @@
+// Internal structures shared by the stage kernels of libtwxi (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include <string>
+#include <vector>
+
+#include "../../include/twxi.h"
+
+namespace twxi {
+
+// ---- constants of the reference arithmetic ------------------------------------------------------------
+// twx/utils/util_geo.py:21-22
+#define TWX_RAD 0.017453292519943295
+#define TWX_EARTH_KM 6371.009
+
+void set_error(const std::string& s);
+extern thread_local long long g_launches;
+
+#define TWXI_CUDA(expr)                                                                         \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            twxi::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                \
+            return TWXI_ERR_CUDA;                                                               \
+        }                                                                                       \
+    } while (0)
+
+#define TWXI_LAUNCH_CHECK()                                                                     \
+    do {                                                                                        \
+        ++twxi::g_launches;                                                                     \
+        cudaError_t _e = cudaGetLastError();                                                    \
+        if (_e != cudaSuccess) {                                                                \
+            twxi::set_error(std::string("kernel launch: ") + cudaGetErrorString(_e));           \
+            return TWXI_ERR_CUDA;                                                               \
+        }                                                                                       \
+    } while (0)
+
+// Device view of one variable's station table (good stations, DB order).
+struct StnTable {
+    int n;
+    const double* lon;      // degrees
+    const double* lat;
+    const double* elev;
+    const double* tdi;
+    const double* lonrad;   // lon * TWX_RAD (one IEEE multiply, same value numpy computes)
+    const double* latrad;
+    const double* coslat;   // cos(latrad)
+    const double* lst;      // [12][n]
+    const double* norm;     // [12][n]
+    const double* optim;    // [12][n]
+    const double* optim_anom;
+    const double* nug;
+    const double* psill;
+    const double* rng;
+    const double* H;        // [n][n] WGS-84 great-circle distance (km) between stations
+};
+
+// Device view of the observations, month-major: position p in [moff[m], moff[m+1]) holds the days of month
+// m+1 in chronological order (StationSerialDataDb.mth_idx, station_data.py:576-580); day_of_pos[p] is the
+// chronological day index.  obsT is station-major [n][ndays] over positions.
+struct ObsTable {
+    int ndays;
+    int moff[13];
+    const float* obsT;
+    const int* day_of_pos;
+    // 1981-2010 normals metadata (interp_tair.py:466-479): chronological runs of (year, month) groups
+    int ngroups;               // (#years in 1981-2010 range covered) * 12, year-major
+    const int* grp_start;      // [ngroups] first chronological day of the group (days are contiguous)
+    const int* grp_len;        // [ngroups] number of days (0 -> mean of empty = NaN)
+};
+
+// Query batch on the device (one variable).  q indexes points; all arrays sized for `cap` points.
+struct Batch {
+    int npts = 0, cap = 0, k1 = 0, k1cap = 0, n_rm = 0, rm_zero = 0, ndays_cap = 0;
+    double *lat = nullptr, *lon = nullptr, *elev = nullptr, *tdi = nullptr, *lst = nullptr;   // lst [cap][12]
+    int32_t* rm_idx = nullptr;     // [cap][TWXI_MAX_RM]
+    int32_t* idx = nullptr;        // [cap][k1]
+    double* dist = nullptr;        // [cap][k1]
+    double* h0 = nullptr;          // [cap][k1]  WGS-84 distance point -> candidate
+    int32_t* nn = nullptr;         // [cap][24]  k_norm[12], k_anom[12]
+    double* vario = nullptr;       // [cap][12][3]
+    double* mean = nullptr;        // [cap][12]
+    double* var = nullptr;         // [cap][12]
+    int32_t* status = nullptr;     // [cap] first failure code (atomicCAS from TWXI_ST_OK)
+    double* daily = nullptr;       // [cap][ndays] chronological order
+};
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = 0;
+    int n = 0;
+    std::vector<void*> owned;      // device allocations freed at destroy
+    StnTable st{};
+    ObsTable ob{};
+    bool has_obs = false;
+    std::vector<void*> obs_owned;
+    double* climdivs = nullptr;
+    int n_climdivs = -1;           // -1: no check
+    Batch b;
+    int max_optim = 0;             // largest finite optim_nnghs / optim_nnghs_anom value
+};
+
+// ---- stage launchers (each enqueues on ctx.stream) ----------------------------------------------------
+int launch_knn(Ctx& c, int npts, const double* lat, const double* lon, const int32_t* rm_idx, int n_rm,
+               int rm_zero, int k1, int32_t* idx, double* dist, double* wgt, int32_t* status);
+int launch_nngh_params(Ctx& c, Batch& b, const int32_t* norm_override, const int32_t* anom_override, int only_mth,
+                       int need_norm, int need_anom, int need_vario);
+int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override);
+int launch_gwr(Ctx& c, Batch& b, int mth, const double* pt_norm_override, int write_daily,
+               double* out_month, int kmax, int32_t* hat_k, int32_t* hat_idx, double* hat_z);
+int launch_build_dist_table(cudaStream_t s, int n, const double* lon, const double* lat, double* H);
+int launch_station_trig(cudaStream_t s, int n, const double* lon, const double* lat, double* lonrad,
+                        double* latrad, double* coslat);
+int launch_unpack_chunk(cudaStream_t s, const double* wrk, int ny, int nx, const double* cd_a, int n_a,
+                        const double* cd_b, int n_b, Batch& bmin, Batch& bmax);
+int launch_cells_status(cudaStream_t s, int ncell, const double* climdiv, const double* cd_a, int n_a,
+                        const double* cd_b, int n_b, int32_t* sa, int32_t* sb);
+int launch_fixer(Ctx& cmin, Ctx& cmax, int ncells, int fix_invalid, int have_daily, uint8_t* status,
+                 double* nmin, double* nmax, double* semin, double* semax,
+                 int16_t* qmin, int16_t* qmax, float* fnmin, float* fnmax, float* fsemin, float* fsemax,
+                 int32_t* ninvalid);
+int launch_finalize_points(Ctx& c, Batch& b, double* daily, double* norms, double* se, double* var_out,
+                           uint8_t* status);
+int launch_status_to_u8(cudaStream_t s, int n, const int32_t* in, uint8_t* out);
+int launch_gather_month(cudaStream_t s, int npts, int mth0, const int32_t* st, const double* src12, double* dst);
+
+// ---- small device helpers -----------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_max_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Haversine "a" term with the reference's operation order and no FMA contraction
+// (util_geo.py:32-36): sin(dlat/2)**2 + cos(lat1)*cos(lat2)*sin(dlon/2)**2
+__device__ __forceinline__ double hav_a(double lat1rad, double lon1rad, double coslat1, double lat2rad,
+                                        double lon2rad, double coslat2) {
+    double dlat = __dsub_rn(lat1rad, lat2rad);
+    double dlon = __dsub_rn(lon1rad, lon2rad);
+    double s1 = sin(dlat / 2);
+    double s2 = sin(dlon / 2);
+    double t = __dmul_rn(__dmul_rn(coslat1, coslat2), __dmul_rn(s2, s2));
+    return __dadd_rn(__dmul_rn(s1, s1), t);
+}
+// util_geo.py:36-39: 6371.009 * (2 * arcsin(sqrt(a)))
+__device__ __forceinline__ double hav_km(double a) {
+    return __dmul_rn(TWX_EARTH_KM, __dmul_rn(2.0, asin(sqrt(a))));
+}
+
+// WGS-84 great-circle distance (km) of sp::gcdist / gstat for long-lat data (Andoyer-Lambert form)
+__device__ __forceinline__ double gcdist_sp(double lon1, double lat1, double lon2, double lat2) {
+    const double DE2RA = 3.14159265358979323846 / 180.0;
+    const double a = 6378.137;
+    const double f = 1.0 / 298.257223563;
+    const double eps = 2.220446049250313e-16;
+    if (fabs(lat1 - lat2) < eps) {
+        if (fabs(lon1 - lon2) < eps) return 0.0;
+        if (fabs((fabs(lon1) + fabs(lon2)) - 360.0) < eps) return 0.0;
+    }
+    double lat1R = lat1 * DE2RA, lat2R = lat2 * DE2RA, lon1R = lon1 * DE2RA, lon2R = lon2 * DE2RA;
+    double F = (lat1R + lat2R) / 2.0;
+    double G = (lat1R - lat2R) / 2.0;
+    double L = (lon1R - lon2R) / 2.0;
+    double sG, cG, sF, cF, sL, cL;
+    sincos(G, &sG, &cG);
+    sincos(F, &sF, &cF);
+    sincos(L, &sL, &cL);
+    double sinG2 = sG * sG, cosG2 = cG * cG, sinF2 = sF * sF, cosF2 = cF * cF, sinL2 = sL * sL, cosL2 = cL * cL;
+    double S = sinG2 * cosL2 + cosF2 * sinL2;
+    double C = cosG2 * cosL2 + sinF2 * sinL2;
+    double w = atan(sqrt(S / C));
+    double R = sqrt(S * C) / w;
+    double D = 2 * w * a;
+    double H1 = (3 * R - 1) / (2 * C);
+    double H2 = (3 * R + 1) / (2 * S);
+    return D * (1 + f * H1 * sinF2 * cosG2 - f * H2 * cosF2 * sinG2);
+}
+
+}  // namespace twxi

@@ -223,6 +223,12 @@ int64_t twxi_launch_count(int reset);
 int twxi_set_stage_timing(int enable);
 int twxi_get_stage_ms(float* ms5);
 
+/*
+ * Measured FP64 peak of `device` in TFLOP/s: tensor-core DMMA (mma.sync.m8n8k4.f64) and scalar DFMA loops.
+ * bench.py uses the DMMA figure as the roofline denominator of the kriging kernel.
+ */
+int twxi_measure_fp64_peak(int device, double* dmma_tflops, double* dfma_tflops);
+
 #ifdef __cplusplus
 }
 #endif

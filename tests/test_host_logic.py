@@ -1,0 +1,93 @@
+"""Host-side logic that needs no GPU: synthetic inputs, the station-DB container, Tiler / partitioning."""
+import numpy as np
+import pytest
+
+from topowx_b200 import synth, db
+from topowx_b200.interp.tiling import Tiler, partition_chunks
+
+
+@pytest.fixture(scope="module")
+def small_db():
+    return synth.make_station_db(0, 300, synth.tile_bbox(buf=1.0), synth.Fields(), synth.make_days(1995, 1))
+
+
+def test_station_db_contract(small_db, tmp_path):
+    d = small_db
+    assert d.var.dtype == np.float32 and d.var.shape == (365, d.stns.size)
+    assert list(d.stn_ids) == sorted(d.stn_ids)                   # DB order is station-id order
+    assert sum(d.mth_idx[m].size for m in range(1, 13)) == 365 and d.mth_idx[2].size == 28
+    ids = d.stn_ids[[5, 2, 9]]
+    obs = d.load_obs(ids, mth=3)
+    assert obs.shape == (31, 3)
+    assert np.array_equal(obs, d.var[d.mth_idx[3]][:, [2, 5, 9]])   # columns come back in DB order
+    assert d.load_obs(d.stn_ids[4]).shape == (365,)
+    p = str(tmp_path / "db.npz")
+    d.save(p)
+    d2 = db.StationSerialDataDb(p, "tmin")
+    assert np.array_equal(d2.var, d.var) and np.array_equal(d2.stn_ids, d.stn_ids)
+    assert np.array_equal(d2.days[db.YMD], d.days[db.YMD])
+    for name in d.stns.dtype.names[3:]:
+        assert np.array_equal(d2.stns[name], d.stns[name], equal_nan=True)
+
+
+def test_synthetic_inputs_shape(small_db):
+    s = small_db.stns
+    assert np.isnan(s[db.BAD]).mean() > 0.9                        # "good" == isnan(bad)
+    assert set(np.unique(s[db.get_optim_varname(1)][np.isfinite(s[db.get_optim_varname(1)])])) <= set(synth.NNGH_SET)
+    f = synth.Fields()
+    w = synth.make_wrk_chk(f, synth.TILE_ROW0, synth.TILE_COL0, 50, 50)
+    assert w.shape == (32, 50, 50) and w[2].all()
+    assert np.all(np.diff(w[3][:, 0]) < 0) and np.all(np.diff(w[4][0]) > 0)      # lat descends, lon ascends
+    assert abs(w[3][0, 0] - (50.0 - (synth.TILE_ROW0 + 0.5) / 120.0)) < 1e-12
+    # no exact distance ties between stations (jittered, no lattice)
+    d2 = (s[db.LON][:, None] - s[db.LON][None, :]) ** 2 + (s[db.LAT][:, None] - s[db.LAT][None, :]) ** 2
+    assert np.unique(d2[np.triu_indices(s.size, 1)]).size == s.size * (s.size - 1) // 2
+
+
+def _tiler(mask=None):
+    ny, nx = 20, 30
+    lats = 45.0 - np.arange(ny) * 0.1
+    lons = -110.0 + np.arange(nx) * 0.1
+    mask = np.ones((ny, nx), bool) if mask is None else mask
+    attrs = [("a%d" % i, np.full((ny, nx), float(i)) + np.arange(nx)[None, :]) for i in range(27)]
+    return Tiler(dict(mask=mask, lon=lons, lat=lats), attrs, 10, 10, 5, 5), lats, lons
+
+
+def test_tiler_chunks_match_reference_order():
+    t, lats, lons = _tiler()
+    assert t.ntiles == 6 and t.ntile_chks == 24 and t.chk_size_i == 32
+    assert t.tile_ids[0] == "h00v00" and t.tile_ids[4] == "h01v01"
+    assert t.tile_chks[0] == (0, 0, 0, 0, 0) and t.tile_chks[1] == (0, 0, 0, 0, 5) and t.tile_chks[4] == (1, 0, 10, 0, 0)
+    k, w = t.next()
+    assert k == 0 and w.shape == (32, 5, 5)
+    assert np.array_equal(w[0], np.mgrid[0:5, 0:5][0]) and np.array_equal(w[1], np.mgrid[0:5, 0:5][1])
+    assert np.all(w[2] == 1) and np.allclose(w[3][:, 0], lats[:5]) and np.allclose(w[4][0], lons[:5])
+    assert np.allclose(w[5 + 3], 3.0 + np.arange(5)[None, :])
+    n = 1
+    for _ in t:
+        n += 1
+    assert n == 24
+    info = t.build_tile_grid_info()
+    assert info.chks_per_tile == 4 and info.nchks == 24 and info.get_tile_id(5) == "h02v01"
+
+
+def test_tiler_skips_empty_tiles_and_partitions():
+    mask = np.ones((20, 30), bool)
+    mask[:10, 10:20] = False                                        # tile 1 fully masked -> skipped
+    mask[10:, :10] = False
+    mask[10:15, 0:3] = True                                         # tile with only 15 cells
+    t, _, _ = _tiler(mask)
+    assert t.ntiles == 5 and sorted(set(c[0] for c in t.tile_chks)) == [0, 1, 2, 3, 4]
+    parts = partition_chunks(t.tile_chks, t.mask, 10, 10, 2)
+    assert sorted(parts[0] + parts[1]) == sorted(t.tile_chks)
+    assert not set(c[0] for c in parts[0]) & set(c[0] for c in parts[1])   # whole tiles
+    load = [sum(int(t.mask[c[1] + c[3]:c[1] + c[3] + 5, c[2] + c[4]:c[2] + c[4] + 5].sum()) for c in p) for p in parts]
+    assert abs(load[0] - load[1]) <= 100
+    assert partition_chunks(t.tile_chks, t.mask, 10, 10, 2, rank=1) == parts[1]
+    one = partition_chunks(t.tile_chks, t.mask, 10, 10, 1)
+    assert one[0] == t.tile_chks
+
+
+def test_tiler_rejects_bad_sizes():
+    with pytest.raises(ValueError):
+        Tiler(dict(mask=np.ones((20, 30), bool), lon=np.arange(30.), lat=np.arange(20.)), [], 7, 10, 5, 5)

@@ -31,7 +31,6 @@
 namespace twxi {
 
 constexpr int KED_HDR = 128 + 8 + 32 + 3 * 128;   // doubles: inv(L_KK) tile, neighbour indices (256 ints), scalars, 2^(j/32)
-constexpr int KED_TPW = 3;              // max tiles of one block column held by one warp
 constexpr int KED_MAXNB = 32;           // size classes NBv = 1..32 (n <= 255)
 
 struct KedArgs {
@@ -210,14 +209,14 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 
 // acc[s] += A_s[J] * B[J]' for J in [0, nj) over the LAST NT slots: the DMMA inner loop of the left-looking update
-template <int NT>
-__device__ __forceinline__ void accumulate(double2 (&acc)[KED_TPW], const double2* const (&pA)[KED_TPW],
+template <int TPW, int NT>
+__device__ __forceinline__ void accumulate(double2 (&acc)[TPW], const double2* const (&pA)[TPW],
                                            const double2* pB, int nj) {
 #pragma unroll 2
     for (int J = 0; J < nj; ++J) {
         const double2 b = pB[J * 32];
 #pragma unroll
-        for (int t = KED_TPW - NT; t < KED_TPW; ++t) {
+        for (int t = TPW - NT; t < TPW; ++t) {
             const double2 av = pA[t][J * 32];
             dmma(acc[t], av.x, b.x);
             dmma(acc[t], av.y, b.y);
@@ -225,6 +224,19 @@ __device__ __forceinline__ void accumulate(double2 (&acc)[KED_TPW], const double
     }
 }
 
+
+template <int TPW, int NT>
+struct AccDispatch {
+    static __device__ __forceinline__ void run(int nact, double2 (&acc)[TPW], const double2* const (&pA)[TPW],
+                                               const double2* pB, int nj) {
+        if (nact == NT) accumulate<TPW, NT>(acc, pA, pB, nj);
+        else AccDispatch<TPW, NT - 1>::run(nact, acc, pA, pB, nj);
+    }
+};
+template <int TPW>
+struct AccDispatch<TPW, 0> {
+    static __device__ __forceinline__ void run(int, double2 (&)[TPW], const double2* const (&)[TPW], const double2*, int) {}
+};
 
 // 5x5 GLS from S = B'V^-1B held by one warp in C-fragment layout: mean and variance of the kriging predictor
 __device__ __forceinline__ void ked_finish(const KedArgs& a, double2 s0, int q, int m, double yref, double c00, int lane) {
@@ -289,28 +301,31 @@ __device__ __forceinline__ void ked_finish(const KedArgs& a, double2 s0, int q, 
 // One stage of a worker warp.  `cur` holds my tiles of column K (all updates but the last one applied), `nxt`
 // receives my tiles of column K+1 with the updates of columns 0..K-1 applied.  The two register sets are swapped
 // by the caller every stage (no copies).
+template <int TPW>
 struct WorkerCtx {
     double2* tl2;          // lane's fragment pointer into the shared L tiles
     const double2* hc2;    // lane's fragment pointer into the compact distance tiles of this point
     double2 *Wt2, *Ct2, *Dt2;
     const int* flag;
     const double* tab32;
-    int I[KED_TPW], rb[KED_TPW], hb[KED_TPW];
+    int I[TPW], rb[TPW], hb[TPW];
     int v, cnt, NBv, n, lane, r8, q4;
     CovPar cp;
 };
 
-template <int NW>
-__device__ __forceinline__ bool worker_stage(const WorkerCtx& x, int K, int rbK, double2 (&cur)[KED_TPW],
-                                             double2 (&nxt)[KED_TPW]) {
+template <int NW, int TPW>
+__device__ __forceinline__ bool worker_stage(const WorkerCtx<TPW>& x, int K, int rbK, double2 (&cur)[TPW],
+                                             double2 (&nxt)[TPW]) {
     constexpr int NTHREADS = (NW + 1) * 32;
-    const int nact = (x.I[0] > K) + (x.I[1] > K) + (x.I[2] > K);     // active rows are the last nact slots
+    int nact = 0;                                             // active rows are the last nact slots
+#pragma unroll
+    for (int s = 0; s < TPW; ++s) nact += (x.I[s] > K);
     // (1) last update of column K (from column K-1, stored at the end of the previous stage)
     if (K >= 1) {
         const double2 b = x.tl2[(rbK + K - 1) * 32];
 #pragma unroll
-        for (int s = 0; s < KED_TPW; ++s) {
-            if (s >= KED_TPW - nact) {
+        for (int s = 0; s < TPW; ++s) {
+            if (s >= TPW - nact) {
                 const double2 av = x.tl2[(x.rb[s] + K - 1) * 32];
                 double2 t = make_double2(0.0, 0.0);
                 dmma(t, av.x, b.x);
@@ -320,35 +335,36 @@ __device__ __forceinline__ bool worker_stage(const WorkerCtx& x, int K, int rbK,
         }
     }
     if (K % NW == x.v) {                                      // I own row K+1: hand tile (K+1, K) to the diagonal warp
-        const int sl = KED_TPW - x.cnt + K / NW;
-        x.Ct2[(K & 1) * 32 + x.lane] = sl == 0 ? cur[0] : (sl == 1 ? cur[1] : cur[2]);
+        const int sl = TPW - x.cnt + K / NW;
+        double2 cs = cur[0];
+#pragma unroll
+        for (int s = 1; s < TPW; ++s) cs = (sl == s) ? cur[s] : cs;
+        x.Ct2[(K & 1) * 32 + x.lane] = cs;
     }
     // (2)-(4) column K+1: fetch its tiles (incl. the diagonal one if I own row K+1), accumulate the updates from
     // columns 0..K-1 and evaluate the covariances
     const int Kn = K + 1;
     const int rbKn = rbK + K;                                 // ltile(K+1, 0)
     if (Kn < x.NBv) {
-        double2 raw[KED_TPW];
-        const double2* pA[KED_TPW];
+        double2 raw[TPW];
+        const double2* pA[TPW];
         const double2* pB = x.tl2 + rbKn * 32;
 #pragma unroll
-        for (int s = 0; s < KED_TPW; ++s) {
+        for (int s = 0; s < TPW; ++s) {
             nxt[s] = make_double2(0.0, 0.0);
             raw[s] = make_double2(0.0, 0.0);
             pA[s] = x.tl2 + x.rb[s] * 32;
-            if (s >= KED_TPW - nact) {
+            if (s >= TPW - nact) {
                 if (x.I[s] < x.NBv) raw[s] = x.hc2[(x.hb[s] + Kn) * 32];
                 else raw[s] = x.tl2[(x.rb[s] + Kn) * 32];
             }
         }
         if (K >= 1) {
-            if (nact == 1) accumulate<1>(nxt, pA, pB, K);
-            else if (nact == 2) accumulate<2>(nxt, pA, pB, K);
-            else if (nact == 3) accumulate<3>(nxt, pA, pB, K);
+            AccDispatch<TPW, TPW>::run(nact, nxt, pA, pB, K);
         }
 #pragma unroll
-        for (int s = 0; s < KED_TPW; ++s) {
-            if (s >= KED_TPW - nact) {
+        for (int s = 0; s < TPW; ++s) {
+            if (s >= TPW - nact) {
                 double2 vt = raw[s];
                 if (x.I[s] < x.NBv)
                     vt = cov_tile(raw[s], 8 * x.I[s] + x.r8, 8 * Kn + 2 * x.q4, x.n, x.cp, x.tab32,
@@ -363,8 +379,8 @@ __device__ __forceinline__ bool worker_stage(const WorkerCtx& x, int K, int rbK,
     if (x.flag[0]) return false;
     const double2 w = x.Wt2[(K & 1) * 32 + x.lane];
 #pragma unroll
-    for (int s = 0; s < KED_TPW; ++s) {
-        if (s >= KED_TPW - nact) {                            // panel solve L_IK = A_IK * inv(L_KK)'
+    for (int s = 0; s < TPW; ++s) {
+        if (s >= TPW - nact) {                            // panel solve L_IK = A_IK * inv(L_KK)'
             double2 l = make_double2(0.0, 0.0);
             dmma(l, cur[s].x, w.x);
             dmma(l, cur[s].y, w.y);
@@ -380,8 +396,8 @@ __device__ __forceinline__ bool worker_stage(const WorkerCtx& x, int K, int rbK,
 // next diagonal tile D_{K+1} = Dt_{K+1} - L_{K+1,K} L_{K+1,K}' itself.  Warps 0..WARPS-2 ("workers") own the tile
 // rows below the diagonal; while the diagonal warp factors column K they accumulate the updates of column K+1
 // that do not depend on column K (including Dt_{K+1}) and evaluate its covariances.
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, (WARPS == 4 ? 8 : 4)) ked_kernel(KedArgs a) {
+template <int WARPS, int TPW, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) ked_kernel(KedArgs a) {
     extern __shared__ double sm[];
     int* sidx = reinterpret_cast<int*>(sm);                   // 256 ints
     int* flag = reinterpret_cast<int*>(sm + 128);             // [0] singular, [1] problem slot
@@ -504,14 +520,14 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 4 ? 8 : 4)) ked_kernel(K
 
             // Row ownership: worker v owns tile rows I = v+1, v+1+NW, v+1+2NW (<= NBv), kept in the LAST slots so
             // that the rows still active at stage K (I > K) are always a suffix of the slot array.
-            WorkerCtx x;
+            WorkerCtx<TPW> x;
             x.tl2 = tl2; x.hc2 = hc2; x.Wt2 = Wt2; x.Ct2 = Ct2; x.Dt2 = Dt2; x.flag = flag; x.tab32 = tab32;
             x.v = v; x.NBv = NBv; x.n = n; x.lane = lane; x.r8 = r8; x.q4 = q4; x.cp = cp;
             x.cnt = (v + 1 <= NBv) ? (NBv - (v + 1)) / NW + 1 : 0;
-            double2 ta[KED_TPW], tb[KED_TPW];                 // ping-pong: tiles of the current / next column
+            double2 ta[TPW], tb[TPW];                 // ping-pong: tiles of the current / next column
 #pragma unroll
-            for (int s = 0; s < KED_TPW; ++s) {
-                const int j = s - (KED_TPW - x.cnt);
+            for (int s = 0; s < TPW; ++s) {
+                const int j = s - (TPW - x.cnt);
                 x.I[s] = j >= 0 ? v + 1 + j * NW : 0;
                 x.rb[s] = x.I[s] * (x.I[s] - 1) / 2;          // ltile(I, 0)
                 x.hb[s] = x.I[s] * (x.I[s] + 1) / 2;          // htile(I, 0)
@@ -527,10 +543,10 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 4 ? 8 : 4)) ked_kernel(K
 
             int rbK = 0;                                      // ltile(K, 0), maintained incrementally
             for (int K = 0; K < NBv; K += 2) {
-                if (!worker_stage<NW>(x, K, rbK, ta, tb)) break;
+                if (!worker_stage<NW, TPW>(x, K, rbK, ta, tb)) break;
                 rbK += K;
                 if (K + 1 >= NBv) break;
-                if (!worker_stage<NW>(x, K + 1, rbK, tb, ta)) break;
+                if (!worker_stage<NW, TPW>(x, K + 1, rbK, tb, ta)) break;
                 rbK += K + 1;
             }
             named_bar_sync(5, NTHREADS);
@@ -538,9 +554,20 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 4 ? 8 : 4)) ked_kernel(K
     }
 }
 
-// worker warps = WARPS-1 own ceil((NBv-K)/(WARPS-1)) <= KED_TPW tiles of a column
-static int ked_warps_for(int nbv) { return nbv <= 9 ? 4 : 8; }
+// Launch configurations: worker warps = WARPS-1 each own up to TPW tile rows: NBv <= (WARPS-1) * TPW.
+struct KedCfg { int warps, tpw, minb; };
+static KedCfg ked_cfg_for(int nbv) {
+    if (nbv <= 9) return {4, 3, 8};
+    return {8, 3, 4};                      // measured: 7 thin workers beat 3 fat ones (more latency hiding)
+}
 static size_t ked_smem_for(int nbv) { return (size_t)(KED_HDR + (nbv * (nbv + 1) / 2) * 64) * sizeof(double); }
+template <typename F>
+static int ked_for_each_kernel(F f) {
+    int rc;
+    if ((rc = f((const void*)ked_kernel<4, 3, 8>)) != 0) return rc;
+    if ((rc = f((const void*)ked_kernel<8, 3, 4>)) != 0) return rc;
+    return 0;
+}
 
 struct KedWork {                 // device scratch of the kriging stage, owned per thread
     double* hc = nullptr;
@@ -560,12 +587,11 @@ int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
         TWXI_CUDA(cudaGetDeviceProperties(&p, c.device));
         w.sms = p.multiProcessorCount;
         TWXI_CUDA(cudaMalloc((void**)&w.bins, 4 * (KED_MAXNB + 1) * sizeof(int32_t)));
-        for (int nbv = 1; nbv <= KED_MAXNB; ++nbv) {
-            const int smem = (int)ked_smem_for(nbv);
-            if (smem > 227 * 1024) break;
-            TWXI_CUDA(cudaFuncSetAttribute(ked_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            TWXI_CUDA(cudaFuncSetAttribute(ked_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        }
+        const int smem_max = (int)ked_smem_for(21);
+        int rc = ked_for_each_kernel([&](const void* k) {
+            return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max) == cudaSuccess ? 0 : 1;
+        });
+        if (rc) { set_error("cudaFuncSetAttribute(ked_kernel) failed"); return TWXI_ERR_CUDA; }
     }
     const int nbmax = (b.k1 - 1 + 7) / 8;                    // largest possible n is k1 - 1
     if (ked_smem_for(nbmax) > 227 * 1024 || nbmax > 21) { set_error("neighbour count too large for the kriging kernel"); return TWXI_ERR_LIMIT; }
@@ -614,12 +640,12 @@ int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
         for (int nbv = nbmax; nbv >= 1; --nbv) {
             a.nbv = nbv;
             const size_t smem = ked_smem_for(nbv);
-            const int warps = ked_warps_for(nbv);
-            int occ = (int)std::min<size_t>((size_t)(227 * 1024) / (smem + 1024), (size_t)(warps == 4 ? 8 : 4));   // smem / register limits
+            const KedCfg cfg = ked_cfg_for(nbv);
+            int occ = (int)std::min<size_t>((size_t)(227 * 1024) / (smem + 1024), (size_t)cfg.minb);   // smem / register limits
             occ = std::max(1, occ);
             const int grid = std::min(w.sms * occ, std::max(1, nt));
-            if (warps == 4) ked_kernel<4><<<grid, 128, smem, c.stream>>>(a);
-            else ked_kernel<8><<<grid, 256, smem, c.stream>>>(a);
+            if (cfg.warps == 4) ked_kernel<4, 3, 8><<<grid, 128, smem, c.stream>>>(a);
+            else ked_kernel<8, 3, 4><<<grid, 256, smem, c.stream>>>(a);
             TWXI_LAUNCH_CHECK();
         }
     }

@@ -1,0 +1,233 @@
+'''
+Classes and functions for performing Tair interpolation: the `twx.interp.interp_tair` interface
+(twx/interp/interp_tair.py) with every numerical stage running on the GPU through libtwxi.
+
+Kept, with the reference's signatures: KrigTair, GwrTairAnom, InterpTair, PtInterpTair, StationDataWrkChk,
+build_empty_pt (tmin_tmax_fixer runs inside the CUDA library: twxi_interp_cells / twxi_interp_chunk).  New batch entry points (no reference equivalent): InterpTair.interp_batch,
+PtInterpTair.interp_chunk.  Not rebuilt (out of the hot path): KrigTairAll,
+BuildKrigParams (variogram fitting in R/gstat), PredictorGrids / interp_to_lonlat (raster I/O), GwrTairAnomR,
+GwrTairNorm.
+'''
+
+__all__ = ["GwrTairAnom", 'KrigTair', 'InterpTair', 'StationDataWrkChk', 'PtInterpTair']
+
+import numpy as np
+
+from .station_select import StationSelect
+from ..db import LON, LAT, ELEV, TDI, LST, BAD, MASK, CLIMDIV, YEAR, MONTH, STN_ID, \
+    StationSerialDataDb, get_norm_varname, get_optim_varname, get_lst_varname, get_optim_anom_varname
+from .. import _lib
+from .. import context as _context
+
+KRIG_TREND_VARS = (LON, LAT, ELEV, LST)
+GWR_TREND_VARS = (LON, LAT, ELEV, TDI, LST)
+LST_TMAX = 'lst_tmax'
+LST_TMIN = 'lst_tmin'
+DFLT_INIT_NNGHS = 100
+_CI_CRITVAL = -1.959963984540054        # scipy.stats.norm.ppf(0.025) (interp_tair.py:792)
+
+
+def _raise_status(st):
+    st = int(st)
+    if st == _lib.ST_OK:
+        return
+    if st == _lib.ST_TOO_FEW_STNS:
+        raise IndexError(_lib.STATUS_MESSAGES[st])
+    if st == _lib.ST_CLIMDIV:
+        raise KeyError(_lib.STATUS_MESSAGES[st])
+    if st == _lib.ST_SINGULAR:
+        raise FloatingPointError(_lib.STATUS_MESSAGES[st])
+    raise Exception(_lib.STATUS_MESSAGES.get(st, "interpolation failed (status %d)" % st))
+
+
+def _pt_lst(pt):
+    return np.array([pt[get_lst_varname(m)] for m in range(1, 13)], dtype=np.float64)
+
+
+def build_empty_pt():
+    ptDtype = [(LON, np.float64), (LAT, np.float64), (ELEV, np.float64),
+               (TDI, np.float64), (CLIMDIV, np.float64), (MASK, np.float64)]
+    ptDtype.extend([("tmin%02d" % mth, np.float64) for mth in np.arange(1, 13)])
+    ptDtype.extend([("tmax%02d" % mth, np.float64) for mth in np.arange(1, 13)])
+    ptDtype.extend([(get_norm_varname(mth), np.float64) for mth in np.arange(1, 13)])
+    ptDtype.extend([(get_optim_varname(mth), np.float64) for mth in np.arange(1, 13)])
+    ptDtype.extend([(get_lst_varname(mth), np.float64) for mth in np.arange(1, 13)])
+    ptDtype.extend([(get_optim_anom_varname(mth), np.float64) for mth in np.arange(1, 13)])
+    a_pt = np.empty(1, dtype=ptDtype)
+    return a_pt[0]
+
+
+class GwrTairAnom(object):
+    '''
+    Geographically weighted regression interpolation of daily temperature anomalies for a month
+    (interp_tair.py:215-314).
+    '''
+
+    def __init__(self, stn_slct):
+        self.stn_slct = stn_slct
+
+    def gwr_mth(self, pt, mth, nnghs=None, stns_rm=None):
+        '''
+        Interpolates the daily anomalies of month `mth` with GWR, adds them to pt's monthly normal
+        (pt[normMM]) and returns the daily values of that month (interp_tair.py:261-314).
+        '''
+        ss = self.stn_slct
+        ctx = ss.ctx
+        vals, st = ctx.gwr_mth(pt[LAT], pt[LON], pt[ELEV], pt[TDI], _pt_lst(pt), int(mth),
+                               pt[get_norm_varname(mth)], nnghs=nnghs, rm_idx=ctx.rm_indices(stns_rm),
+                               rm_zero=ss.rm_zero_dist_stns)
+        _raise_status(st[0])
+        return vals[0]
+
+
+class KrigTair(object):
+    '''
+    Moving window regression kriging of monthly normals with variogram parameters passed in or smoothed
+    from the neighboring stations (interp_tair.py:770-926).  The R/gstat call is replaced by the CUDA
+    kriging-with-external-drift kernel.
+    '''
+
+    def __init__(self, stn_slct):
+        self.stn_slct = stn_slct
+        self.ci_critval = _CI_CRITVAL
+
+    def std_err_ci(self, tair_mean, tair_var):
+        std_err = np.sqrt(tair_var) if tair_var >= 0 else 0
+        ci_r = np.abs(std_err * self.ci_critval)
+        return std_err, (tair_mean - ci_r, tair_mean + ci_r)
+
+    def krig(self, pt, mth, nnghs=None, vario_params=None, stns_rm=None):
+        '''
+        Returns (tair_mean, tair_var) for month `mth` at `pt` (interp_tair.py:853-926).
+        '''
+        ss = self.stn_slct
+        ctx = ss.ctx
+        mean, var, st = ctx.krig(pt[LAT], pt[LON], pt[ELEV], _pt_lst(pt), mth=int(mth), nnghs=nnghs,
+                                 vario=vario_params, rm_idx=ctx.rm_indices(stns_rm), rm_zero=ss.rm_zero_dist_stns)
+        _raise_status(st[0])
+        return float(mean[0, 0]), float(var[0, 0])
+
+
+class InterpTair(object):
+    '''
+    Monthly normals (moving window regression kriging) and daily temperatures (GWR) for a single
+    temperature variable (interp_tair.py:371-439).
+    '''
+
+    def __init__(self, krig_tair, gwr_tair):
+        self.krig_tair = krig_tair
+        self.gwr_tair = gwr_tair
+        self.mth_masks = self.gwr_tair.stn_slct.stn_da.mth_idx
+        self.ndays = self.gwr_tair.stn_slct.stn_da.days.size
+
+    def interp(self, pt, stns_rm=None):
+        '''
+        Returns (tair_daily[ndays], tair_norms[12], tair_se[12]); like the reference it also stores the
+        kriged normals in pt[normMM] (interp_tair.py:433).
+        '''
+        ss = self.gwr_tair.stn_slct
+        ctx = ss.ctx
+        dly, norms, se, var, st = ctx.interp_points(pt[LAT], pt[LON], pt[ELEV], pt[TDI], _pt_lst(pt),
+                                                    rm_idx=ctx.rm_indices(stns_rm), rm_zero=ss.rm_zero_dist_stns)
+        _raise_status(st[0])
+        for mth in range(1, 13):
+            pt[get_norm_varname(mth)] = norms[0, mth - 1]
+        return dly[0], norms[0], se[0]
+
+    def interp_batch(self, lat, lon, elev, tdi, lst, rm_idx=None, daily=True):
+        '''
+        Batch form (new): arrays of points, lst [npts, 12]; rm_idx [npts, n_rm] indices into the selected
+        stations (-1 = none).  Returns (daily [npts, ndays] or None, norms, se, var [npts, 12], status [npts]).
+        '''
+        ss = self.gwr_tair.stn_slct
+        return ss.ctx.interp_points(lat, lon, elev, tdi, lst, rm_idx=rm_idx, rm_zero=ss.rm_zero_dist_stns,
+                                    daily=daily)
+
+
+class PtInterpTair(object):
+    '''
+    Monthly normals and daily temperatures for both Tmin and Tmax (interp_tair.py:441-592).
+    '''
+
+    def __init__(self, stn_da_tmin, stn_da_tmax, aux_fpaths=None, interp_orders=None, norms_only=False, device=0):
+        self.days = stn_da_tmin.days
+        self.stn_da_tmin = stn_da_tmin
+        self.stn_da_tmax = stn_da_tmax
+        daysNormMask = np.nonzero(np.logical_and(self.days[YEAR] >= 1981, self.days[YEAR] <= 2010))[0]
+        if daysNormMask.size == 0:
+            raise IndexError("the observation record has no day within 1981-2010")   # uYrs[0], interp_tair.py:470
+        self.daysNormMask = daysNormMask
+        mask_stns_tmin = np.isnan(stn_da_tmin.stns[BAD])
+        mask_stns_tmax = np.isnan(stn_da_tmax.stns[BAD])
+        stn_slct_tmin = StationSelect(stn_da_tmin, mask_stns_tmin, device=device)
+        stn_slct_tmax = StationSelect(stn_da_tmax, mask_stns_tmax, device=device)
+        self.interp_tmin = InterpTair(KrigTair(stn_slct_tmin), GwrTairAnom(stn_slct_tmin))
+        self.interp_tmax = InterpTair(KrigTair(stn_slct_tmax), GwrTairAnom(stn_slct_tmax))
+        self.ctx_tmin = stn_slct_tmin.ctx
+        self.ctx_tmax = stn_slct_tmax.ctx
+        self.norms_only = norms_only
+        if aux_fpaths is not None:
+            raise NotImplementedError("PredictorGrids / interp_to_lonlat read predictor rasters with netCDF4 + "
+                                      "basemap (interp_tair.py:87-141); raster I/O stays on the reference path")
+        self.a_pt = build_empty_pt()
+
+    def interp_to_lonlat(self, lon, lat, fixInvalid=True, chgLatLon=True, stns_rm=None, elev=None):
+        raise NotImplementedError("raster predictor lookup (PredictorGrids) stays on the reference path; fill "
+                                  "PtInterpTair.a_pt and call interp_pt()")
+
+    def interp_pt(self, fix_invalid=True, stns_rm=None):
+        '''
+        Interpolate daily and monthly normal Tmin and Tmax for the current PtInterpTair.a_pt
+        (interp_tair.py:526-592).  Returns (tmin_dly, tmax_dly, tmin_norms, tmax_norms, tmin_se, tmax_se,
+        ninvalid).
+        '''
+        a_pt = self.a_pt
+        lst_tmin = np.array([a_pt["tmin%02d" % m] for m in range(1, 13)], dtype=np.float64)
+        lst_tmax = np.array([a_pt["tmax%02d" % m] for m in range(1, 13)], dtype=np.float64)
+        rm_a = self.ctx_tmin.rm_indices(stns_rm)
+        rm_b = self.ctx_tmax.rm_indices(stns_rm)
+        if rm_a is not None or rm_b is not None:
+            raise NotImplementedError("stns_rm with two station databases: use InterpTair.interp per variable")
+        r = _context.interp_cells(self.ctx_tmin, self.ctx_tmax, a_pt[LAT], a_pt[LON], a_pt[ELEV], a_pt[TDI],
+                                  a_pt[CLIMDIV], lst_tmin, lst_tmax, fix_invalid=fix_invalid)
+        tmin, tmax, nmin, nmax, semin, semax, ninv, st = r
+        _raise_status(st[0])
+        for m in range(1, 13):                                    # side effects of the reference (:562-575, :433)
+            a_pt[get_lst_varname(m)] = a_pt["tmax%02d" % m]
+            a_pt[get_norm_varname(m)] = nmax[0, m - 1]
+        return tmin[0], tmax[0], nmin[0], nmax[0], semin[0], semax[0], int(ninv[0]) if fix_invalid else 0
+
+    def interp_chunk(self, wrk_chk, out=None):
+        '''
+        Batch form (new): one work chunk f8[32, ny, nx] exactly as Tiler.next() builds it (tiling.py:205-213);
+        replaces the per-cell loop of step25_mpi_interp_tair.py:126-175.  Returns the step25 result buffers
+        (tmin/tmax int16 [ndays, ny, nx], *_norm/*_se float32 [12, ny, nx], ninvalid int32, status uint8).
+        '''
+        return _context.interp_chunk(self.ctx_tmin, self.ctx_tmax, wrk_chk, out=out, daily=not self.norms_only)
+
+
+class StationDataWrkChk(StationSerialDataDb):
+    '''
+    StationSerialDataDb wrapper that preloads the observations of a lon/lat box (interp_tair.py:997-1097).
+    On the GPU path the whole observation table is resident in HBM, so set_obs only records the box; load_obs
+    keeps the reference's contract (columns in DB order) for callers that want host arrays.
+    '''
+
+    def __init__(self, nc_path, var_name, vcc_size=None, vcc_nelems=None, vcc_preemption=None):
+        StationSerialDataDb.__init__(self, nc_path, var_name, vcc_size, vcc_nelems, vcc_preemption)
+        self.chk_stnids = None
+        self.chk_obs = None
+        self.chk_deg_buf = None
+        self.chk_bnds = None
+
+    def set_obs(self, bnds, deg_buf=3):
+        minLat, maxLat = bnds[0] - deg_buf, bnds[1] + deg_buf
+        minLon, maxLon = bnds[2] - deg_buf, bnds[3] + deg_buf
+        maskStns = np.logical_and(np.logical_and(self.stns[LAT] >= minLat, self.stns[LAT] <= maxLat),
+                                  np.logical_and(self.stns[LON] >= minLon, self.stns[LON] <= maxLon))
+        self.chk_stnids = np.take(self.stn_ids, np.nonzero(maskStns)[0])
+        self.chk_deg_buf = deg_buf
+        self.chk_bnds = bnds
+
+    def load_obs(self, stn_ids, mth=None):
+        return StationSerialDataDb.load_obs(self, stn_ids, mth)

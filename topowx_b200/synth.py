@@ -33,8 +33,9 @@ class Fields(object):
     these functions sampled at cell centres and station predictors are the same functions sampled at
     the station (the reference extracts raster values at stations, ``post_infill.py:248-352``)."""
 
-    def __init__(self, seed=SEED_RASTERS, noctaves=5):
+    def __init__(self, seed=SEED_RASTERS, noctaves=5, dtr_override=None):
         rng = np.random.default_rng(seed)
+        self.dtr_override = dtr_override     # constant diurnal range (tests of the Tmin>=Tmax fixer)
 
         def waves(n, lam_min, lam_max):
             lam = np.exp(rng.uniform(np.log(lam_min), np.log(lam_max), n))    # wavelength in degrees
@@ -92,13 +93,18 @@ class Fields(object):
     def dtr(self, mth, lon, lat):
         """Mean diurnal range of the synthetic station normals; small in winter in part of the
         domain so that a little of the interpolated output has Tmin >= Tmax (exercises the fixer)."""
-        return np.maximum(0.6, 7.0 + 3.5 * self._season(mth) + 3.5 * self._sum(self.w_dtr, lon, lat))
+        if self.dtr_override is not None:
+            return np.full(np.shape(lon), float(self.dtr_override))
+        return np.maximum(0.6, 5.6 + 5.0 * self._season(mth) + 3.5 * self._sum(self.w_dtr, lon, lat))
 
     def tair_norm(self, which, mth, lon, lat, elev, lst):
-        """Monthly normal 'truth': linear trend in the kriging predictors + smooth residual."""
+        """Monthly normal 'truth': linear trend in the kriging predictors + smooth residual.  Tmax - Tmin equals
+        dtr() up to the (variable-specific) smooth residuals, whatever the night/day LST difference."""
+        lst_n = self.lst(0, mth, lon, lat, elev)
+        lst_d = self.lst(1, mth, lon, lat, elev)
         tavg = (11.0 + 11.5 * self._season(mth) - 0.0048 * elev - 0.55 * (np.asarray(lat) - 38.0)
-                + 0.05 * (np.asarray(lon) + 98.0) + 0.18 * (lst - 14.0)
-                + 0.8 * self._sum(self.w_res[which], lon, lat))
+                + 0.05 * (np.asarray(lon) + 98.0) + 0.18 * (lst - 14.0) - 0.18 * ((lst_d if which else lst_n) - 0.5 * (lst_n + lst_d))
+                + 0.5 * self._sum(self.w_res[which], lon, lat))
         half = 0.5 * self.dtr(mth, lon, lat)
         return tavg + (half if which else -half)
 

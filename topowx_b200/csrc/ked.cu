@@ -14,23 +14,32 @@
 //  1. hgather: per point, the station-station distances of its nmax = max_m k_norm nearest stations are
 //     gathered ONCE from the N x N table into a compact buffer of row-major 8x8 tiles (lower block triangle,
 //     neighbours in distance-rank order so every month's set is a leading block).  The 12 monthly systems then
-//     stream their tiles with coalesced 16-byte loads instead of re-gathering 32-byte sectors per pair.
-//  2. bin/scan/scatter: (point, month) problems are counting-sorted by NBv = ceil(n/8) so that each size class
+//     stream their tiles with bulk copies instead of re-gathering 32-byte sectors per pair.
+//  2. bin/scan/scatter: (point, month) problems are counting-sorted by NB = ceil(n/8) so that each size class
 //     is launched with exactly the shared memory it needs (occupancy 6 CTAs/SM at n ~ 80, 2 at n = 147).
-//  3. ked: persistent CTAs pull problems of one size class from an atomic cursor.  The augmented symmetric
-//     matrix [[V, B], [B', 0]] is eliminated with a LEFT-looking blocked Cholesky on 8x8 FP64 tiles: a tile of
-//     block column K is built in registers (V = C(h) evaluated on the fly), receives all its updates
-//     A_IK -= L_IJ L_KJ' as FP64 tensor-core MMAs (mma.sync.m8n8k4.f64, "DMMA") accumulating in registers, the
-//     diagonal tile is factored and inverted inside one warp with shuffles, the panel solve
-//     L_IK = A_IK inv(L_KK)' is two more DMMAs, and only then the tile is written to shared memory — once.
-//     A tile held in the MMA C-fragment layout (lane = 4*row + col/2 holds two adjacent columns) serves directly
-//     as the A operand and as the transposed B operand of two k=4 steps (even columns, then odd columns), so
-//     tiles never need re-layout.  The last tile row holds B' (7 rows); its diagonal tile ends up as -S.
+//  3. ked (v3): persistent CTAs, one problem at a time per CTA, problems strided statically over the CTAs of the
+//     size class (the next problem's descriptor is prefetched).  The augmented symmetric matrix [[V, B], [B', 0]]
+//     is eliminated with a LEFT-looking blocked Cholesky on 8x8 FP64 tiles held in the mma C-fragment layout
+//     (lane = 4*row + col/2 holds two adjacent columns): such a tile serves directly as the A operand and as the
+//     transposed B operand of two mma.sync.m8n8k4.f64 ("DMMA") steps, so X*Y' is two DMMAs and tiles never need
+//     re-layout.  Tile row NB holds B' (7 rows); its diagonal tile ends up as S.
+//     Data flow per problem (N := sum L L' - V, the negated Schur complement, so DMMAs accumulate in place):
+//       prologue   one thread issues a TMA bulk copy (cp.async.bulk + mbarrier) per tile row that lands the raw
+//                  distance tiles straight in the shared-memory slots of L; meanwhile all warps build B'; then
+//                  columns 0 and 1 of N are generated (covariances evaluated in place).
+//       stage K    diagonal warp: W = inv(chol(D_K)) with shuffles (serial chain), publish -W; ONE CTA barrier;
+//                  then it forms D_{K+1} itself from N(K+1,K) and -W (4-6 DMMAs) and goes on factoring.
+//                  workers (rows dealt round-robin per stage, two rows at a time for independent DMMA chains):
+//                  phase A  L(I,K) = N(I,K)(-W)'; N(I,K+1) += L(I,K-1)L(K+1,K-1)' + L(I,K)L(K+1,K)' (final)
+//                  phase B  look-ahead: N(I,K+2) = sum_{J<K} L(I,J)L(K+2,J)' - C(h(I,K+2)), covariance evaluated
+//                           from the raw distances waiting in that very slot.
+//     Nothing lives in registers across stages, every loop is rolled and free of per-slot predicates, and the
+//     only synchronisation is one bar.sync per block column.
 #include "twxi_internal.cuh"
 
 namespace twxi {
 
-constexpr int KED_HDR = 128 + 8 + 32 + 3 * 128;   // doubles: inv(L_KK) tile, neighbour indices (256 ints), scalars, 2^(j/32)
+constexpr int KED_HDR = 128 + 8 + 32 + 2 * 128;   // doubles: neighbour indices (256 ints), flag + mbarrier, 2^(j/32), -inv(L_KK) x2, N_diag x2
 constexpr int KED_MAXNB = 32;           // size classes NBv = 1..32 (n <= 255)
 
 struct KedArgs {
@@ -47,10 +56,9 @@ struct KedArgs {
     const double* qlst;        // [npts][12]
     const double* hc;          // compact distance tiles of points q0.. (stride hc_stride doubles per point)
     size_t hc_stride;
-    const int32_t* list;       // problem ids (q*12 + m) sorted by size class
+    const int2* list;          // (problem id q*12 + m, n) sorted by size class
     const int32_t* bstart;     // [KED_MAXNB+1]
     const int32_t* bcount;
-    int32_t* cursor;           // [KED_MAXNB+1]
     int nbv;                   // size class of this launch
     double* mean;              // [npts][12]
     double* var;
@@ -58,13 +66,28 @@ struct KedArgs {
 };
 
 __device__ __forceinline__ void dmma(double2& c, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c.x), "+d"(c.y) : "d"(a), "d"(b));
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c.x), "+d"(c.y) : "d"(a), "d"(b));
+}
+// c += X * Y' for two 8x8 tiles in C-fragment layout (even columns, then odd columns)
+__device__ __forceinline__ void dmma2(double2& c, const double2& x, const double2& y) {
+    dmma(c, x.x, y.x);
+    dmma(c, x.y, y.y);
 }
 // shared-memory L tiles: rows 1..NBv, row I holds tiles J = 0..I-1 (diagonal tiles are never stored)
 __device__ __forceinline__ int ltile(int I, int J) { return I * (I - 1) / 2 + J; }
 // compact distance tiles: rows 0..NB-1, row I holds tiles J = 0..I
 __device__ __forceinline__ int htile(int I, int J) { return I * (I + 1) / 2 + J; }
+
+// 1/d for a normal positive double without the slow-path branches of the IEEE division: MUFU seed (~2^-20) and one
+// third-order Newton step (error ~ e^3, below 1 ulp).  Non-positive / non-finite pivots are rejected by the caller.
+__device__ __forceinline__ double fast_rcp(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    const double e = fma(-d, r, 1.0);
+    const double e2 = fma(e, e, e);
+    return fma(r, e2, r);
+}
 
 // Factor the 8x8 SPD tile held in C-fragment layout by one warp and return W = inv(L), L = its Cholesky factor
 // (lower triangular, same layout).  lane = 4*r + q holds columns 2q, 2q+1 of row r.  Computed as an LDL'
@@ -86,7 +109,7 @@ __device__ __forceinline__ bool chol8_inverse(double2 a, double2& w, int lane) {
         const double cj0 = __shfl_sync(0xffffffffu, mine, 4 * (2 * q) + kq);       // a[2q][k]
         const double cj1 = __shfl_sync(0xffffffffu, mine, 4 * (2 * q + 1) + kq);   // a[2q+1][k]
         ok = ok && (dk > 0.0);                                // NaN fails; inf is caught by the final isfinite
-        const double p = 1.0 / dk;
+        const double p = fast_rcp(dk);
         if (r == k) prow = p;
         const double t0 = ci * cj0, t1 = ci * cj1;
         if (2 * q > k) a.x = fma(-t0, p, a.x);
@@ -141,14 +164,14 @@ __global__ void ked_bin_kernel(int q0, int nq, int single_mth, const int32_t* nn
     if (n < 1) return;
     atomicAdd(&bcount[(n + 7) >> 3], 1);
 }
-__global__ void ked_scan_kernel(const int32_t* bcount, int32_t* bstart, int32_t* fill, int32_t* cursor) {
+__global__ void ked_scan_kernel(const int32_t* bcount, int32_t* bstart, int32_t* fill) {
     if (threadIdx.x == 0) {
         int s = 0;
-        for (int b = 0; b <= KED_MAXNB; ++b) { bstart[b] = s; s += bcount[b]; fill[b] = 0; cursor[b] = 0; }
+        for (int b = 0; b <= KED_MAXNB; ++b) { bstart[b] = s; s += bcount[b]; fill[b] = 0; }
     }
 }
 __global__ void ked_scatter_kernel(int q0, int nq, int single_mth, const int32_t* nn, const int32_t* status,
-                                   const int32_t* bstart, int32_t* fill, int32_t* list) {
+                                   const int32_t* bstart, int32_t* fill, int2* list) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nq * 12) return;
     const int q = q0 + t / 12, m = t % 12;
@@ -157,7 +180,7 @@ __global__ void ked_scatter_kernel(int q0, int nq, int single_mth, const int32_t
     const int n = nn[(size_t)q * 24 + m];
     if (n < 1) return;
     const int b = (n + 7) >> 3;
-    list[bstart[b] + atomicAdd(&fill[b], 1)] = q * 12 + m;
+    list[bstart[b] + atomicAdd(&fill[b], 1)] = make_int2(q * 12 + m, n);
 }
 
 // ---- 3. the solve ------------------------------------------------------------------------------------------------
@@ -192,7 +215,7 @@ __device__ __forceinline__ double cov(double h, const CovPar& cp, const double* 
 // V tile (I, K) from its distance tile in C-fragment layout; lane holds (i, j) and (i, j+1).
 // `plain` (warp-uniform): the tile is strictly below the diagonal and inside the n x n block, so no masking.
 __device__ __forceinline__ double2 cov_tile(double2 h, int i, int j, int n, const CovPar& cp, const double* tab32,
-                                            bool plain = false) {
+                                            bool plain) {
     double2 v;
     v.x = cov(h.x, cp, tab32);
     v.y = cov(h.y, cp, tab32);
@@ -207,36 +230,26 @@ __device__ __forceinline__ double2 cov_tile(double2 h, int i, int j, int n, cons
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-
-// acc[s] += A_s[J] * B[J]' for J in [0, nj) over the LAST NT slots: the DMMA inner loop of the left-looking update
-template <int TPW, int NT>
-__device__ __forceinline__ void accumulate(double2 (&acc)[TPW], const double2* const (&pA)[TPW],
-                                           const double2* pB, int nj) {
-#pragma unroll 2
-    for (int J = 0; J < nj; ++J) {
-        const double2 b = pB[J * 32];
-#pragma unroll
-        for (int t = TPW - NT; t < TPW; ++t) {
-            const double2 av = pA[t][J * 32];
-            dmma(acc[t], av.x, b.x);
-            dmma(acc[t], av.y, b.y);
-        }
-    }
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* mbar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-
-
-template <int TPW, int NT>
-struct AccDispatch {
-    static __device__ __forceinline__ void run(int nact, double2 (&acc)[TPW], const double2* const (&pA)[TPW],
-                                               const double2* pB, int nj) {
-        if (nact == NT) accumulate<TPW, NT>(acc, pA, pB, nj);
-        else AccDispatch<TPW, NT - 1>::run(nact, acc, pA, pB, nj);
-    }
-};
-template <int TPW>
-struct AccDispatch<TPW, 0> {
-    static __device__ __forceinline__ void run(int, double2 (&)[TPW], const double2* const (&)[TPW], const double2*, int) {}
-};
+__device__ __forceinline__ void mbar_expect_tx(void* mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* mbar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_u32(mbar)), "r"(parity) : "memory");
+    } while (!done);
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on the mbarrier (bytes and addresses multiples of 16)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, void* mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
+}
 
 // 5x5 GLS from S = B'V^-1B held by one warp in C-fragment layout: mean and variance of the kriging predictor
 __device__ __forceinline__ void ked_finish(const KedArgs& a, double2 s0, int q, int m, double yref, double c00, int lane) {
@@ -244,7 +257,7 @@ __device__ __forceinline__ void ked_finish(const KedArgs& a, double2 s0, int q, 
 #pragma unroll
     for (int r = 0; r < 7; ++r)
 #pragma unroll
-        for (int cc = 0; cc < 7; ++cc)
+        for (int cc = 0; cc <= r; ++cc)
             S[r][cc] = __shfl_sync(0xffffffffu, (cc & 1) ? s0.y : s0.x, 4 * r + (cc >> 1));
     if (lane != 0) return;
     double G[5][5], gy[5], rr[5], t[5], dinv[5];
@@ -298,286 +311,283 @@ __device__ __forceinline__ void ked_finish(const KedArgs& a, double2 s0, int q, 
     }
 }
 
-// One stage of a worker warp.  `cur` holds my tiles of column K (all updates but the last one applied), `nxt`
-// receives my tiles of column K+1 with the updates of columns 0..K-1 applied.  The two register sets are swapped
-// by the caller every stage (no copies).
-template <int TPW>
-struct WorkerCtx {
-    double2* tl2;          // lane's fragment pointer into the shared L tiles
-    const double2* hc2;    // lane's fragment pointer into the compact distance tiles of this point
-    double2 *Wt2, *Ct2, *Dt2;
-    const int* flag;
+// Per-problem view shared by the phases of one warp
+struct Prob {
+    double2* tl2;          // lane's fragment pointer into the shared L / N tiles: tile t is tl2[t * 32]
+    double2* Nd2;          // lane's fragment of the two N_diag buffers: Nd2[(c & 1) * 32]
+    const double2* hc2;    // lane's fragment pointer into the compact distance tiles of this point (global)
     const double* tab32;
-    int I[TPW], rb[TPW], hb[TPW];
-    int v, cnt, NBv, n, lane, r8, q4;
     CovPar cp;
+    int NB, n, r8, q4;
 };
 
-template <int NW, int TPW>
-__device__ __forceinline__ bool worker_stage(const WorkerCtx<TPW>& x, int K, int rbK, double2 (&cur)[TPW],
-                                             double2 (&nxt)[TPW]) {
-    constexpr int NTHREADS = (NW + 1) * 32;
-    int nact = 0;                                             // active rows are the last nact slots
-#pragma unroll
-    for (int s = 0; s < TPW; ++s) nact += (x.I[s] > K);
-    // (1) last update of column K (from column K-1, stored at the end of the previous stage)
-    if (K >= 1) {
-        const double2 b = x.tl2[(rbK + K - 1) * 32];
-#pragma unroll
-        for (int s = 0; s < TPW; ++s) {
-            if (s >= TPW - nact) {
-                const double2 av = x.tl2[(x.rb[s] + K - 1) * 32];
-                double2 t = make_double2(0.0, 0.0);
-                dmma(t, av.x, b.x);
-                dmma(t, av.y, b.y);
-                cur[s].x -= t.x; cur[s].y -= t.y;
-            }
-        }
+// N(I, c) = acc - V(I, c), stored to its slot (or to the N_diag buffer when I == c).  `hd` = raw distances of the
+// diagonal tile (c, c), only read when I == c < NB.  All branches are warp-uniform.
+__device__ __forceinline__ void finish_tile(const Prob& p, int I, int c, double2 acc, double2 hd) {
+    const int slot = (ltile(I, 0) + c) * 32;
+    double2 v;
+    if (I == p.NB) {
+        v = (c == p.NB) ? make_double2(0.0, 0.0) : p.tl2[slot];                    // raw B' tile
+    } else if (I == c) {
+        v = cov_tile(hd, 8 * I + p.r8, 8 * c + 2 * p.q4, p.n, p.cp, p.tab32, false);
+    } else {
+        v = cov_tile(p.tl2[slot], 8 * I + p.r8, 8 * c + 2 * p.q4, p.n, p.cp, p.tab32, 8 * I + 8 <= p.n);
     }
-    if (K % NW == x.v) {                                      // I own row K+1: hand tile (K+1, K) to the diagonal warp
-        const int sl = TPW - x.cnt + K / NW;
-        double2 cs = cur[0];
-#pragma unroll
-        for (int s = 1; s < TPW; ++s) cs = (sl == s) ? cur[s] : cs;
-        x.Ct2[(K & 1) * 32 + x.lane] = cs;
-    }
-    // (2)-(4) column K+1: fetch its tiles (incl. the diagonal one if I own row K+1), accumulate the updates from
-    // columns 0..K-1 and evaluate the covariances
-    const int Kn = K + 1;
-    const int rbKn = rbK + K;                                 // ltile(K+1, 0)
-    if (Kn < x.NBv) {
-        double2 raw[TPW];
-        const double2* pA[TPW];
-        const double2* pB = x.tl2 + rbKn * 32;
-#pragma unroll
-        for (int s = 0; s < TPW; ++s) {
-            nxt[s] = make_double2(0.0, 0.0);
-            raw[s] = make_double2(0.0, 0.0);
-            pA[s] = x.tl2 + x.rb[s] * 32;
-            if (s >= TPW - nact) {
-                if (x.I[s] < x.NBv) raw[s] = x.hc2[(x.hb[s] + Kn) * 32];
-                else raw[s] = x.tl2[(x.rb[s] + Kn) * 32];
-            }
-        }
-        if (K >= 1) {
-            AccDispatch<TPW, TPW>::run(nact, nxt, pA, pB, K);
-        }
-#pragma unroll
-        for (int s = 0; s < TPW; ++s) {
-            if (s >= TPW - nact) {
-                double2 vt = raw[s];
-                if (x.I[s] < x.NBv)
-                    vt = cov_tile(raw[s], 8 * x.I[s] + x.r8, 8 * Kn + 2 * x.q4, x.n, x.cp, x.tab32,
-                                  x.I[s] > Kn && 8 * x.I[s] + 8 <= x.n);
-                nxt[s].x = vt.x - nxt[s].x;
-                nxt[s].y = vt.y - nxt[s].y;
-                if (x.I[s] == Kn) x.Dt2[(Kn & 1) * 32 + x.lane] = nxt[s];         // next diagonal tile
-            }
-        }
-    }
-    named_bar_sync(2, NTHREADS);                              // #1: inv(L_KK) ready
-    if (x.flag[0]) return false;
-    const double2 w = x.Wt2[(K & 1) * 32 + x.lane];
-#pragma unroll
-    for (int s = 0; s < TPW; ++s) {
-        if (s >= TPW - nact) {                            // panel solve L_IK = A_IK * inv(L_KK)'
-            double2 l = make_double2(0.0, 0.0);
-            dmma(l, cur[s].x, w.x);
-            dmma(l, cur[s].y, w.y);
-            x.tl2[(x.rb[s] + K) * 32] = l;
-        }
-    }
-    named_bar_sync(3, NW * 32);                               // #2 (workers): column K of L visible
-    return true;
+    acc.x -= v.x; acc.y -= v.y;
+    if (I == c) p.Nd2[(c & 1) * 32] = acc;
+    else p.tl2[slot] = acc;
 }
 
-// Warp-specialised pipeline.  The LAST warp (highest issue priority among the CTA's warps) runs nothing but the
-// serial chain of the diagonal tiles: for column K it factors D_K, publishes inv(L_KK), and immediately forms the
-// next diagonal tile D_{K+1} = Dt_{K+1} - L_{K+1,K} L_{K+1,K}' itself.  Warps 0..WARPS-2 ("workers") own the tile
-// rows below the diagonal; while the diagonal warp factors column K they accumulate the updates of column K+1
-// that do not depend on column K (including Dt_{K+1}) and evaluate its covariances.
-template <int WARPS, int TPW, int MINB>
-__global__ void __launch_bounds__(WARPS * 32, MINB) ked_kernel(KedArgs a) {
-    extern __shared__ double sm[];
+// Look-ahead: column c of N over the terms J < nj, rows c + w, c + w + NWP, ... (two rows per pass)
+template <int NWP>
+__device__ __forceinline__ void phase_b(const Prob& p, int c, int nj, int w, double2 hd) {
+    const double2* pB = p.tl2 + ltile(c, 0) * 32;
+    int I = c + w;
+    for (; I + NWP <= p.NB; I += 2 * NWP) {
+        const double2* pA1 = p.tl2 + ltile(I, 0) * 32;
+        const double2* pA2 = p.tl2 + ltile(I + NWP, 0) * 32;
+        double2 acc1 = make_double2(0.0, 0.0), acc2 = make_double2(0.0, 0.0);
+#pragma unroll 2
+        for (int J = 0; J < nj; ++J) {
+            const double2 b = pB[J * 32], a1 = pA1[J * 32], a2 = pA2[J * 32];
+            dmma(acc1, a1.x, b.x); dmma(acc2, a2.x, b.x);
+            dmma(acc1, a1.y, b.y); dmma(acc2, a2.y, b.y);
+        }
+        finish_tile(p, I, c, acc1, hd);
+        finish_tile(p, I + NWP, c, acc2, hd);
+    }
+    if (I <= p.NB) {
+        const double2* pA1 = p.tl2 + ltile(I, 0) * 32;
+        double2 acc1 = make_double2(0.0, 0.0), acc2 = make_double2(0.0, 0.0);
+        int J = 0;
+        for (; J + 1 < nj; J += 2) {                          // two accumulators: independent DMMA chains
+            const double2 b0 = pB[J * 32], a0 = pA1[J * 32], b1 = pB[J * 32 + 32], a1 = pA1[J * 32 + 32];
+            dmma(acc1, a0.x, b0.x); dmma(acc2, a1.x, b1.x);
+            dmma(acc1, a0.y, b0.y); dmma(acc2, a1.y, b1.y);
+        }
+        if (J < nj) dmma2(acc1, pA1[J * 32], pB[J * 32]);
+        acc1.x += acc2.x; acc1.y += acc2.y;
+        finish_tile(p, I, c, acc1, hd);
+    }
+}
+
+// Panel solve of column K and the last two updates of column K+1 for rows K+2+w, K+2+w+NW, ...
+//   L(I,K) = N(I,K) (-W)';  N(I,K+1) += L(I,K-1) L(K+1,K-1)' + L(I,K) L(K+1,K)'
+template <int NW>
+__device__ __forceinline__ void phase_a(const Prob& p, int K, int w, const double2 negW, const double2 lk1, const double2 bK) {
+    double2* tl2 = p.tl2;
+    int I = K + 2 + w;
+    for (; I + NW <= p.NB; I += 2 * NW) {
+        const int s1 = (ltile(I, 0) + K) * 32, s2 = (ltile(I + NW, 0) + K) * 32;
+        const double2 n1 = tl2[s1], n2 = tl2[s2];
+        double2 c1 = tl2[s1 + 32], c2 = tl2[s2 + 32];
+        double2 l1 = make_double2(0.0, 0.0), l2 = make_double2(0.0, 0.0);
+        dmma(l1, n1.x, negW.x); dmma(l2, n2.x, negW.x);
+        dmma(l1, n1.y, negW.y); dmma(l2, n2.y, negW.y);
+        if (K >= 1) {
+            const double2 a1 = tl2[s1 - 32], a2 = tl2[s2 - 32];
+            dmma(c1, a1.x, bK.x); dmma(c2, a2.x, bK.x);
+            dmma(c1, a1.y, bK.y); dmma(c2, a2.y, bK.y);
+        }
+        tl2[s1] = l1; tl2[s2] = l2;
+        dmma(c1, l1.x, lk1.x); dmma(c2, l2.x, lk1.x);
+        dmma(c1, l1.y, lk1.y); dmma(c2, l2.y, lk1.y);
+        tl2[s1 + 32] = c1; tl2[s2 + 32] = c2;
+    }
+    if (I <= p.NB) {
+        const int s1 = (ltile(I, 0) + K) * 32;
+        const double2 n1 = tl2[s1];
+        double2 c1 = tl2[s1 + 32];
+        double2 l1 = make_double2(0.0, 0.0);
+        dmma2(l1, n1, negW);
+        if (K >= 1) dmma2(c1, tl2[s1 - 32], bK);
+        tl2[s1] = l1;
+        dmma2(c1, l1, lk1);
+        tl2[s1 + 32] = c1;
+    }
+}
+
+template <int NW, int MINB>
+__global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
+    extern __shared__ __align__(16) double sm[];
     int* sidx = reinterpret_cast<int*>(sm);                   // 256 ints
-    int* flag = reinterpret_cast<int*>(sm + 128);             // [0] singular, [1] problem slot
+    int* flag = reinterpret_cast<int*>(sm + 128);             // [0] singular
+    void* mbar = sm + 130;                                    // mbarrier of the distance-tile bulk copies
     double* tab32 = sm + 136;                                 // 32: 2^(j/32)
-    double2* Wt2 = reinterpret_cast<double2*>(sm + 168);      // 2 x 64: inv(L_KK), double-buffered by K & 1
-    double2* Ct2 = reinterpret_cast<double2*>(sm + 296);      // 2 x 64: updated tile (K+1, K) for the diagonal warp
-    double2* Dt2 = reinterpret_cast<double2*>(sm + 424);      // 2 x 64: pre-updated diagonal tile of column K
+    double2* Wt2 = reinterpret_cast<double2*>(sm + 168);      // 2 x 64: -inv(L_KK), double-buffered by K & 1
+    double2* Nd2 = reinterpret_cast<double2*>(sm + 296);      // 2 x 64: N_diag of column c, double-buffered by c & 1
     double* tiles = sm + KED_HDR;
-    constexpr int NTHREADS = WARPS * 32;
-    constexpr int NW = WARPS - 1;                             // worker warps 0..NW-1; warp NW is the diagonal warp
+    constexpr int NT = (NW + 1) * 32;
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);    // warp-uniform by construction
-    const int r8 = lane >> 2, q4 = lane & 3;
-    const int NBv = a.nbv;
-    const int count = a.bcount[NBv], start = a.bstart[NBv];
+    const int NB = a.nbv;
+    const int count = a.bcount[NB], start = a.bstart[NB];
     const int N = a.st.n;
-    double2* tl2 = reinterpret_cast<double2*>(tiles) + lane;  // lane's fragment of tile t: tl2[t * 32]
     if (tid < 32) tab32[tid] = exp2((double)tid / 32.0);
-    // the 5x5 solve of a finished problem is deferred by the diagonal warp into the prologue of the next one,
-    // where the workers are busy building B' and column 0 anyway
+    if (tid == 0) mbar_init(mbar, 1);
+    uint32_t parity = 0;
+
+    Prob p;
+    p.tl2 = reinterpret_cast<double2*>(tiles) + lane;
+    p.Nd2 = Nd2 + lane;
+    p.tab32 = tab32;
+    p.NB = NB; p.r8 = lane >> 2; p.q4 = lane & 3;
+    double2* const tl2 = p.tl2;
+    const uint32_t tx_bytes = (uint32_t)(NB * (NB - 1) / 2) * 512u;     // tile rows 1..NB-1, I tiles each
+
+    // the 5x5 solve of a finished problem is deferred by the diagonal warp into the prologue of the next one
     bool pending = false;
     double2 pend_S = make_double2(0.0, 0.0);
     int pend_q = 0, pend_m = 0;
     double pend_yref = 0.0, pend_c00 = 0.0;
 
-    for (;;) {
+    int slot = blockIdx.x;
+    int2 desc = slot < count ? a.list[start + slot] : make_int2(0, 0);
+    for (; slot < count; slot += gridDim.x) {
+        const int pid = desc.x, n = desc.y;
+        if (slot + (int)gridDim.x < count) desc = a.list[start + slot + gridDim.x];   // prefetch the next descriptor
+        const int q = pid / 12, m = pid - q * 12;
+        p.n = n;
+        p.hc2 = reinterpret_cast<const double2*>(a.hc + (size_t)(q - a.q0) * a.hc_stride) + lane;
         __syncthreads();                                      // previous problem: shared memory fully consumed
-        if (tid == 0) { flag[1] = atomicAdd(a.cursor + NBv, 1); flag[0] = 0; }
-        __syncthreads();
-        const int slot = flag[1];
+        if (tid == 0) {
+            flag[0] = 0;
+            if (tx_bytes) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(mbar, tx_bytes);
+                const double* src = a.hc + (size_t)(q - a.q0) * a.hc_stride;
+                for (int I = 1; I < NB; ++I)
+                    bulk_g2s(tiles + ltile(I, 0) * 64, src + htile(I, 0) * 64, (uint32_t)I * 512u, mbar);
+            }
+        }
+        for (int j = tid; j < n; j += NT) sidx[j] = a.idx[(size_t)q * a.k1 + j];
+        const double* vp = a.vario_is_override ? a.vario + (size_t)q * 3 : a.vario + ((size_t)q * 12 + m) * 3;
+        const double nug = vp[0], psill = vp[1], rng = vp[2];
+        p.cp.c00 = nug + psill;
+        p.cp.psill_eff = rng != 0.0 ? psill : 0.0;            // range == 0: pure nugget model (interp.R:223-227)
+        p.cp.nir = rng != 0.0 ? -1.0 / rng : 0.0;
+        // raw distances of the diagonal tiles of columns 0 and 1 (consumed after the B' rows are built)
+        const int wd1 = (NB + 1) % (NW + 1);                  // warp that generates tile (1,1) below
+        double2 hd0 = make_double2(0.0, 0.0), hd1 = make_double2(0.0, 0.0);
+        if (warp == 0) hd0 = p.hc2[0];
+        if (warp == wd1 && NB > 1) hd1 = p.hc2[htile(1, 1) * 32];
         if (warp == NW && pending) {
             ked_finish(a, pend_S, pend_q, pend_m, pend_yref, pend_c00, lane);
             pending = false;
         }
-        if (slot >= count) break;
-        const int pid = a.list[start + slot];
-        const int q = pid / 12, m = pid - q * 12;
-        const int n = a.nn[(size_t)q * 24 + m];
-        const double* vp = a.vario_is_override ? a.vario + (size_t)q * 3 : a.vario + ((size_t)q * 12 + m) * 3;
-        const double nug = vp[0], psill = vp[1], rng = vp[2];
-        CovPar cp;
-        cp.c00 = nug + psill;
-        cp.psill_eff = rng != 0.0 ? psill : 0.0;              // range == 0: pure nugget model (interp.R:223-227)
-        cp.nir = rng != 0.0 ? -1.0 / rng : 0.0;
-        const double2* hc2 = reinterpret_cast<const double2*>(a.hc + (size_t)(q - a.q0) * a.hc_stride) + lane;
+        __syncthreads();                                      // sidx visible
+        // augmented rows B' = [1, dlon, dlat, delev, dlst, y - yref, c0]' into tile row NB
+        {
+            const double lon0 = a.qlon[q], lat0 = a.qlat[q], elev0 = a.qelev[q], lst0 = a.qlst[(size_t)q * 12 + m];
+            const double* lstm = a.st.lst + (size_t)m * N;
+            const double* normm = a.st.norm + (size_t)m * N;
+            const double yref = normm[sidx[0]];
+            double* row = tiles + ltile(NB, 0) * 64;
+            const int cnt = NB * 64;
+            for (int e = tid; e < cnt; e += NT) {
+                const int J = e >> 6, r = (e >> 3) & 7, cidx = e & 7;
+                const int j = 8 * J + cidx;
+                double val = 0.0;
+                if (j < n && r < 7) {
+                    const int s = sidx[j];
+                    if (r == 0) val = 1.0;
+                    else if (r == 1) val = a.st.lon[s] - lon0;
+                    else if (r == 2) val = a.st.lat[s] - lat0;
+                    else if (r == 3) val = (a.st.elev[s] - elev0) * 1e-3;
+                    else if (r == 4) val = (lstm[s] - lst0) * 0.1;
+                    else if (r == 5) val = normm[s] - yref;
+                    else val = cov(a.h0[(size_t)q * a.k1 + j], p.cp, tab32);
+                }
+                row[e] = val;
+            }
+        }
+        if (tx_bytes) mbar_wait(mbar, parity);                // distance tiles have landed in their slots
+        parity ^= 1u;
+        __syncthreads();                                      // B' rows visible
+        // columns 0 and 1 of N (no update terms yet), all warps
+        {
+            const int cnt0 = NB + 1, cnt = cnt0 + NB;         // tiles (I,0), I = 0..NB and (I,1), I = 1..NB
+            for (int it = warp; it < cnt; it += NW + 1) {
+                const int c = it < cnt0 ? 0 : 1;
+                const int I = it < cnt0 ? it : it - cnt0 + 1;
+                finish_tile(p, I, c, make_double2(0.0, 0.0), c == 0 ? hd0 : hd1);
+            }
+        }
+        __syncthreads();
 
         if (warp == NW) {
             // ================= diagonal warp =====================================================================
-            double2 s0 = make_double2(0.0, 0.0);              // S = sum_J L_NJ L_NJ'
+            const double yref = a.st.norm[(size_t)m * N + sidx[0]];
+            double2 D = Nd2[lane];
+            D.x = -D.x; D.y = -D.y;                           // V_00
             bool singular = false;
-            const double yref = a.st.norm[(size_t)m * N + a.idx[(size_t)q * a.k1]];
-            named_bar_sync(1, NTHREADS);                      // prologue of the workers done
-            double2 D = Dt2[lane];                            // V_00
-            const int rbN = ltile(NBv, 0);
-            for (int K = 0; K < NBv; ++K) {
+            for (int K = 0; K < NB; ++K) {
                 double2 w;
                 const bool ok = chol8_inverse(D, w, lane);
+                w.x = -w.x; w.y = -w.y;
                 Wt2[(K & 1) * 32 + lane] = w;
                 if (!ok && lane == 0) flag[0] = 1;
-                named_bar_sync(2, NTHREADS);                  // #1: inv(L_KK) published; Ct/Dt of this stage visible
+                named_bar_sync(1, NT);                        // -inv(L_KK) published; the workers' stage K-1 is complete
                 if (flag[0]) { singular = true; break; }
-                if (K + 1 < NBv) {
-                    const double2 cK = Ct2[(K & 1) * 32 + lane];            // updated tile (K+1, K)
-                    D = Dt2[((K + 1) & 1) * 32 + lane];                     // V - sum_{J<K} for the next diagonal tile
-                    double2 l = make_double2(0.0, 0.0);
-                    dmma(l, cK.x, w.x);
-                    dmma(l, cK.y, w.y);                                     // L_{K+1,K}
-                    double2 u = make_double2(0.0, 0.0);
-                    dmma(u, l.x, l.x);
-                    dmma(u, l.y, l.y);
-                    D.x -= u.x; D.y -= u.y;
-                }
-                if (K >= 1) {                                 // S += L_{N,K-1} L_{N,K-1}' (off the critical path)
-                    const double2 l = tl2[(rbN + K - 1) * 32];
-                    dmma(s0, l.x, l.x); dmma(s0, l.y, l.y);
-                }
+                const int rb = ltile(K + 1, 0);
+                double2 l = make_double2(0.0, 0.0);
+                dmma2(l, tl2[(rb + K) * 32], w);              // L(K+1,K) = N(K+1,K) (-W)'
+                double2 nd = Nd2[((K + 1) & 1) * 32 + lane];
+                if (K >= 1) { const double2 t = tl2[(rb + K - 1) * 32]; dmma2(nd, t, t); }
+                dmma2(nd, l, l);
+                D.x = -nd.x; D.y = -nd.y;                     // D_{K+1}; for K+1 == NB this is -S
             }
-            named_bar_sync(5, NTHREADS);                      // last column of L stored
             if (singular) {
                 if (lane == 0) atomicCAS(a.status + q, TWXI_ST_OK, TWXI_ST_SINGULAR);
-                continue;
+            } else {
+                pend_S = make_double2(-D.x, -D.y);
+                pend_q = q; pend_m = m; pend_yref = yref; pend_c00 = p.cp.c00; pending = true;
             }
-            {
-                const double2 l = tl2[(rbN + NBv - 1) * 32];
-                dmma(s0, l.x, l.x); dmma(s0, l.y, l.y);
-            }
-            pend_S = s0; pend_q = q; pend_m = m; pend_yref = yref; pend_c00 = cp.c00; pending = true;
         } else {
             // ================= worker warps ======================================================================
-            const int v = warp;
-            for (int j = tid; j < n; j += NW * 32) sidx[j] = a.idx[(size_t)q * a.k1 + j];
-            named_bar_sync(4, NW * 32);
-            // augmented rows B' = [1, dlon, dlat, delev, dlst, y - yref, c0]' into tile row NBv
-            {
-                const double lon0 = a.qlon[q], lat0 = a.qlat[q], elev0 = a.qelev[q], lst0 = a.qlst[(size_t)q * 12 + m];
-                const double* lstm = a.st.lst + (size_t)m * N;
-                const double* normm = a.st.norm + (size_t)m * N;
-                const double yref = normm[sidx[0]];
-                double* row = tiles + ltile(NBv, 0) * 64;
-                const int cnt = NBv * 64;
-                for (int e = tid; e < cnt; e += NW * 32) {
-                    const int J = e >> 6, r = (e >> 3) & 7, cidx = e & 7;
-                    const int j = 8 * J + cidx;
-                    double val = 0.0;
-                    if (j < n && r < 7) {
-                        const int s = sidx[j];
-                        if (r == 0) val = 1.0;
-                        else if (r == 1) val = a.st.lon[s] - lon0;
-                        else if (r == 2) val = a.st.lat[s] - lat0;
-                        else if (r == 3) val = (a.st.elev[s] - elev0) * 1e-3;
-                        else if (r == 4) val = (lstm[s] - lst0) * 0.1;
-                        else if (r == 5) val = normm[s] - yref;
-                        else val = cov(a.h0[(size_t)q * a.k1 + j], cp, tab32);
-                    }
-                    row[e] = val;
+            const int w = warp;
+            for (int K = 0; K < NB; ++K) {
+                const int c = K + 2;
+                double2 hd = make_double2(0.0, 0.0);
+                if (w == 0 && c < NB) hd = p.hc2[htile(c, c) * 32];           // diagonal distances of column K+2
+                named_bar_sync(1, NT);
+                if (flag[0]) break;
+                if (c <= NB) {
+                    const double2 negW = Wt2[(K & 1) * 32 + lane];
+                    const int rb = ltile(K + 1, 0);
+                    double2 lk1 = make_double2(0.0, 0.0);
+                    dmma2(lk1, tl2[(rb + K) * 32], negW);     // L(K+1,K), recomputed by every worker
+                    double2 bK = make_double2(0.0, 0.0);
+                    if (K >= 1) bK = tl2[(rb + K - 1) * 32];  // L(K+1,K-1)
+                    phase_a<NW>(p, K, w, negW, lk1, bK);
+                    phase_b<NW>(p, c, K, w, hd);
                 }
             }
-            named_bar_sync(4, NW * 32);                       // B' rows visible to the workers
-
-            // Row ownership: worker v owns tile rows I = v+1, v+1+NW, v+1+2NW (<= NBv), kept in the LAST slots so
-            // that the rows still active at stage K (I > K) are always a suffix of the slot array.
-            WorkerCtx<TPW> x;
-            x.tl2 = tl2; x.hc2 = hc2; x.Wt2 = Wt2; x.Ct2 = Ct2; x.Dt2 = Dt2; x.flag = flag; x.tab32 = tab32;
-            x.v = v; x.NBv = NBv; x.n = n; x.lane = lane; x.r8 = r8; x.q4 = q4; x.cp = cp;
-            x.cnt = (v + 1 <= NBv) ? (NBv - (v + 1)) / NW + 1 : 0;
-            double2 ta[TPW], tb[TPW];                 // ping-pong: tiles of the current / next column
-#pragma unroll
-            for (int s = 0; s < TPW; ++s) {
-                const int j = s - (TPW - x.cnt);
-                x.I[s] = j >= 0 ? v + 1 + j * NW : 0;
-                x.rb[s] = x.I[s] * (x.I[s] - 1) / 2;          // ltile(I, 0)
-                x.hb[s] = x.I[s] * (x.I[s] + 1) / 2;          // htile(I, 0)
-                ta[s] = make_double2(0.0, 0.0);
-                tb[s] = make_double2(0.0, 0.0);
-                if (x.I[s] >= 1) {                            // column 0: no updates yet
-                    if (x.I[s] < NBv) ta[s] = cov_tile(hc2[x.hb[s] * 32], 8 * x.I[s] + r8, 2 * q4, n, cp, tab32);
-                    else ta[s] = tl2[x.rb[s] * 32];
-                }
-            }
-            if (v == 0) Dt2[lane] = cov_tile(hc2[0], r8, 2 * q4, n, cp, tab32);           // V_00
-            named_bar_sync(1, NTHREADS);
-
-            int rbK = 0;                                      // ltile(K, 0), maintained incrementally
-            for (int K = 0; K < NBv; K += 2) {
-                if (!worker_stage<NW, TPW>(x, K, rbK, ta, tb)) break;
-                rbK += K;
-                if (K + 1 >= NBv) break;
-                if (!worker_stage<NW, TPW>(x, K + 1, rbK, tb, ta)) break;
-                rbK += K + 1;
-            }
-            named_bar_sync(5, NTHREADS);
         }
     }
+    if (warp == NW && pending) ked_finish(a, pend_S, pend_q, pend_m, pend_yref, pend_c00, lane);
 }
 
-// Launch configurations: worker warps = WARPS-1 each own up to TPW tile rows: NBv <= (WARPS-1) * TPW.
-struct KedCfg { int warps, tpw, minb; };
-static KedCfg ked_cfg_for(int nbv) {
-    if (nbv <= 9) return {4, 3, 8};
-    return {8, 3, 4};                      // measured: 7 thin workers beat 3 fat ones (more latency hiding)
+// Launch configurations: NW worker warps + the diagonal warp.
+static int ked_nw_for(int nbv) {
+    static int thr = -1;
+    if (thr < 0) { const char* e = getenv("TWXI_KED_NW7_FROM"); thr = e ? atoi(e) : 13; }
+    return nbv >= thr ? 7 : 3;
 }
 static size_t ked_smem_for(int nbv) { return (size_t)(KED_HDR + (nbv * (nbv + 1) / 2) * 64) * sizeof(double); }
-template <typename F>
-static int ked_for_each_kernel(F f) {
-    int rc;
-    if ((rc = f((const void*)ked_kernel<4, 3, 8>)) != 0) return rc;
-    if ((rc = f((const void*)ked_kernel<8, 3, 4>)) != 0) return rc;
-    return 0;
-}
 
 struct KedWork {                 // device scratch of the kriging stage, owned per thread
     double* hc = nullptr;
     size_t hc_bytes = 0;
-    int32_t* list = nullptr;
+    int2* list = nullptr;
     size_t list_cap = 0;
-    int32_t* bins = nullptr;     // bcount | bstart | fill | cursor, each KED_MAXNB+1
+    int32_t* bins = nullptr;     // bcount | bstart | fill, each KED_MAXNB+1
     int sms = 0;
+    int occ[2][KED_MAXNB + 1];   // resident CTAs per SM for (NW = 3 / 7, size class)
 };
 static thread_local KedWork g_ked;
+constexpr int KED_NBMAX = 21;
 
 int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
     if (b.npts <= 0) return TWXI_OK;
@@ -585,16 +595,21 @@ int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
     if (!w.sms) {
         cudaDeviceProp p;
         TWXI_CUDA(cudaGetDeviceProperties(&p, c.device));
+        TWXI_CUDA(cudaMalloc((void**)&w.bins, 3 * (KED_MAXNB + 1) * sizeof(int32_t)));
+        const int smem_max = (int)ked_smem_for(KED_NBMAX);
+        TWXI_CUDA(cudaFuncSetAttribute(ked_kernel<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        TWXI_CUDA(cudaFuncSetAttribute(ked_kernel<7, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        for (int nb = 1; nb <= KED_NBMAX; ++nb) {
+            int o3 = 0, o7 = 0;
+            TWXI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, ked_kernel<3, 8>, 128, ked_smem_for(nb)));
+            TWXI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o7, ked_kernel<7, 4>, 256, ked_smem_for(nb)));
+            w.occ[0][nb] = std::max(1, o3);
+            w.occ[1][nb] = std::max(1, o7);
+        }
         w.sms = p.multiProcessorCount;
-        TWXI_CUDA(cudaMalloc((void**)&w.bins, 4 * (KED_MAXNB + 1) * sizeof(int32_t)));
-        const int smem_max = (int)ked_smem_for(21);
-        int rc = ked_for_each_kernel([&](const void* k) {
-            return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max) == cudaSuccess ? 0 : 1;
-        });
-        if (rc) { set_error("cudaFuncSetAttribute(ked_kernel) failed"); return TWXI_ERR_CUDA; }
     }
     const int nbmax = (b.k1 - 1 + 7) / 8;                    // largest possible n is k1 - 1
-    if (ked_smem_for(nbmax) > 227 * 1024 || nbmax > 21) { set_error("neighbour count too large for the kriging kernel"); return TWXI_ERR_LIMIT; }
+    if (nbmax > KED_NBMAX || ked_smem_for(nbmax) > 227 * 1024) { set_error("neighbour count too large for the kriging kernel"); return TWXI_ERR_LIMIT; }
     const size_t hc_stride = (size_t)nbmax * (nbmax + 1) / 2 * 64;
     // points per sub-batch so that the compact distance buffer stays within its budget
     size_t budget = (size_t)6 << 30;
@@ -609,18 +624,17 @@ int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
     if ((size_t)qcap * 12 > w.list_cap) {
         if (w.list) cudaFree(w.list);
         w.list = nullptr; w.list_cap = 0;
-        TWXI_CUDA(cudaMalloc((void**)&w.list, (size_t)qcap * 12 * sizeof(int32_t)));
+        TWXI_CUDA(cudaMalloc((void**)&w.list, (size_t)qcap * 12 * sizeof(int2)));
         w.list_cap = (size_t)qcap * 12;
     }
-    int32_t *bcount = w.bins, *bstart = w.bins + (KED_MAXNB + 1), *fill = w.bins + 2 * (KED_MAXNB + 1),
-            *cursor = w.bins + 3 * (KED_MAXNB + 1);
+    int32_t *bcount = w.bins, *bstart = w.bins + (KED_MAXNB + 1), *fill = w.bins + 2 * (KED_MAXNB + 1);
     KedArgs a;
     a.st = c.st; a.npts = b.npts; a.k1 = b.k1;
     a.idx = b.idx; a.h0 = b.h0; a.nn = b.nn;
     a.vario = vario_override ? vario_override : b.vario;
     a.vario_is_override = vario_override != nullptr;
     a.qlon = b.lon; a.qlat = b.lat; a.qelev = b.elev; a.qlst = b.lst;
-    a.hc = w.hc; a.hc_stride = hc_stride; a.list = w.list; a.bstart = bstart; a.bcount = bcount; a.cursor = cursor;
+    a.hc = w.hc; a.hc_stride = hc_stride; a.list = w.list; a.bstart = bstart; a.bcount = bcount;
     a.mean = b.mean; a.var = b.var; a.status = b.status;
     const int single = mth >= 1 ? mth - 1 : -1;
     for (int q0 = 0; q0 < b.npts; q0 += qcap) {
@@ -632,7 +646,7 @@ int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
         const int nt = nq * 12;
         ked_bin_kernel<<<(nt + 255) / 256, 256, 0, c.stream>>>(q0, nq, single, b.nn, b.status, bcount);
         TWXI_LAUNCH_CHECK();
-        ked_scan_kernel<<<1, 32, 0, c.stream>>>(bcount, bstart, fill, cursor);
+        ked_scan_kernel<<<1, 32, 0, c.stream>>>(bcount, bstart, fill);
         TWXI_LAUNCH_CHECK();
         ked_scatter_kernel<<<(nt + 255) / 256, 256, 0, c.stream>>>(q0, nq, single, b.nn, b.status, bstart, fill, w.list);
         TWXI_LAUNCH_CHECK();
@@ -640,12 +654,11 @@ int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
         for (int nbv = nbmax; nbv >= 1; --nbv) {
             a.nbv = nbv;
             const size_t smem = ked_smem_for(nbv);
-            const KedCfg cfg = ked_cfg_for(nbv);
-            int occ = (int)std::min<size_t>((size_t)(227 * 1024) / (smem + 1024), (size_t)cfg.minb);   // smem / register limits
-            occ = std::max(1, occ);
+            const bool big = ked_nw_for(nbv) == 7;
+            const int occ = w.occ[big ? 1 : 0][nbv];
             const int grid = std::min(w.sms * occ, std::max(1, nt));
-            if (cfg.warps == 4) ked_kernel<4, 3, 8><<<grid, 128, smem, c.stream>>>(a);
-            else ked_kernel<8, 3, 4><<<grid, 256, smem, c.stream>>>(a);
+            if (big) ked_kernel<7, 4><<<grid, 256, smem, c.stream>>>(a);
+            else ked_kernel<3, 8><<<grid, 128, smem, c.stream>>>(a);
             TWXI_LAUNCH_CHECK();
         }
     }

@@ -35,6 +35,9 @@
 //                           from the raw distances waiting in that very slot.
 //     Nothing lives in registers across stages, every loop is rolled and free of per-slot predicates, and the
 //     only synchronisation is one bar.sync per block column.
+#include <cstdio>
+#include <cstdlib>
+#include <algorithm>
 #include "twxi_internal.cuh"
 
 namespace twxi {
@@ -252,7 +255,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 // 5x5 GLS from S = B'V^-1B held by one warp in C-fragment layout: mean and variance of the kriging predictor
-__device__ __forceinline__ void ked_finish(const KedArgs& a, double2 s0, int q, int m, double yref, double c00, int lane) {
+__device__ __noinline__ void ked_finish(double* mean_out, double* var_out, int32_t* status, double2 s0, int q, int m, double yref, double c00, int lane) {
     double S[7][7];
 #pragma unroll
     for (int r = 0; r < 7; ++r)
@@ -304,10 +307,10 @@ __device__ __forceinline__ void ked_finish(const KedArgs& a, double2 s0, int q, 
 #pragma unroll
     for (int i = 0; i < 5; ++i) { mean = fma(t[i], gy[i], mean); var = fma(rr[i], t[i], var); }
     if (!ok || !isfinite(mean) || !isfinite(var)) {
-        atomicCAS(a.status + q, TWXI_ST_OK, TWXI_ST_SINGULAR);
+        atomicCAS(status + q, TWXI_ST_OK, TWXI_ST_SINGULAR);
     } else {
-        a.mean[(size_t)q * 12 + m] = mean;
-        a.var[(size_t)q * 12 + m] = var;
+        mean_out[(size_t)q * 12 + m] = mean;
+        var_out[(size_t)q * 12 + m] = var;
     }
 }
 
@@ -321,53 +324,60 @@ struct Prob {
     int NB, n, r8, q4;
 };
 
-// N(I, c) = acc - V(I, c), stored to its slot (or to the N_diag buffer when I == c).  `hd` = raw distances of the
-// diagonal tile (c, c), only read when I == c < NB.  All branches are warp-uniform.
-__device__ __forceinline__ void finish_tile(const Prob& p, int I, int c, double2 acc, double2 hd) {
-    const int slot = (ltile(I, 0) + c) * 32;
-    double2 v;
-    if (I == p.NB) {
-        v = (c == p.NB) ? make_double2(0.0, 0.0) : p.tl2[slot];                    // raw B' tile
-    } else if (I == c) {
-        v = cov_tile(hd, 8 * I + p.r8, 8 * c + 2 * p.q4, p.n, p.cp, p.tab32, false);
-    } else {
-        v = cov_tile(p.tl2[slot], 8 * I + p.r8, 8 * c + 2 * p.q4, p.n, p.cp, p.tab32, 8 * I + 8 <= p.n);
-    }
-    acc.x -= v.x; acc.y -= v.y;
-    if (I == c) p.Nd2[(c & 1) * 32] = acc;
-    else p.tl2[slot] = acc;
+// -V(c,c) of a diagonal tile from its raw distances (zero for the S tile c == NB)
+__device__ __forceinline__ double2 neg_cov_diag(const Prob& p, int c, double2 hd) {
+    if (c >= p.NB) return make_double2(0.0, 0.0);
+    const double2 v = cov_tile(hd, 8 * c + p.r8, 8 * c + 2 * p.q4, p.n, p.cp, p.tab32, false);
+    return make_double2(-v.x, -v.y);
 }
 
-// Look-ahead: column c of N over the terms J < nj, rows c + w, c + w + NWP, ... (two rows per pass)
-template <int NWP>
-__device__ __forceinline__ void phase_b(const Prob& p, int c, int nj, int w, double2 hd) {
+// Look-ahead: N(I,c) += sum_{J<nj} L(I,J) L(c,J)' for rows I = c + u, c + u + NW, ... (two rows per pass, even and
+// odd J in separate accumulators: four independent DMMA chains).  The slots already hold -V(I,c) (or -B'); the
+// diagonal tile (I == c) starts from `vd` and goes to the N_diag buffer.
+template <int NW>
+__device__ __forceinline__ void phase_b(const Prob& p, int c, int nj, int u, double2 vd) {
     const double2* pB = p.tl2 + ltile(c, 0) * 32;
-    int I = c + w;
-    for (; I + NWP <= p.NB; I += 2 * NWP) {
-        const double2* pA1 = p.tl2 + ltile(I, 0) * 32;
-        const double2* pA2 = p.tl2 + ltile(I + NWP, 0) * 32;
-        double2 acc1 = make_double2(0.0, 0.0), acc2 = make_double2(0.0, 0.0);
-#pragma unroll 2
-        for (int J = 0; J < nj; ++J) {
-            const double2 b = pB[J * 32], a1 = pA1[J * 32], a2 = pA2[J * 32];
-            dmma(acc1, a1.x, b.x); dmma(acc2, a2.x, b.x);
-            dmma(acc1, a1.y, b.y); dmma(acc2, a2.y, b.y);
+    int I = c + u;
+    for (; I + NW <= p.NB; I += 2 * NW) {
+        const int r1 = ltile(I, 0) * 32, r2 = ltile(I + NW, 0) * 32;
+        const double2* pA1 = p.tl2 + r1;
+        const double2* pA2 = p.tl2 + r2;
+        double2 acc1 = (I == c) ? vd : p.tl2[r1 + c * 32];
+        double2 acc2 = p.tl2[r2 + c * 32];
+        double2 e1 = make_double2(0.0, 0.0), e2 = make_double2(0.0, 0.0);
+        int J = 0;
+        for (; J + 1 < nj; J += 2) {
+            const double2 b0 = pB[J * 32], b1 = pB[J * 32 + 32];
+            const double2 a10 = pA1[J * 32], a11 = pA1[J * 32 + 32];
+            const double2 a20 = pA2[J * 32], a21 = pA2[J * 32 + 32];
+            dmma(acc1, a10.x, b0.x); dmma(acc2, a20.x, b0.x); dmma(e1, a11.x, b1.x); dmma(e2, a21.x, b1.x);
+            dmma(acc1, a10.y, b0.y); dmma(acc2, a20.y, b0.y); dmma(e1, a11.y, b1.y); dmma(e2, a21.y, b1.y);
         }
-        finish_tile(p, I, c, acc1, hd);
-        finish_tile(p, I + NWP, c, acc2, hd);
+        if (J < nj) {
+            const double2 b0 = pB[J * 32], a10 = pA1[J * 32], a20 = pA2[J * 32];
+            dmma(acc1, a10.x, b0.x); dmma(acc2, a20.x, b0.x);
+            dmma(acc1, a10.y, b0.y); dmma(acc2, a20.y, b0.y);
+        }
+        acc1.x += e1.x; acc1.y += e1.y; acc2.x += e2.x; acc2.y += e2.y;
+        if (I == c) p.Nd2[(c & 1) * 32] = acc1;
+        else p.tl2[r1 + c * 32] = acc1;
+        p.tl2[r2 + c * 32] = acc2;
     }
     if (I <= p.NB) {
-        const double2* pA1 = p.tl2 + ltile(I, 0) * 32;
-        double2 acc1 = make_double2(0.0, 0.0), acc2 = make_double2(0.0, 0.0);
+        const int r1 = ltile(I, 0) * 32;
+        const double2* pA1 = p.tl2 + r1;
+        double2 acc1 = (I == c) ? vd : p.tl2[r1 + c * 32];
+        double2 e1 = make_double2(0.0, 0.0);
         int J = 0;
-        for (; J + 1 < nj; J += 2) {                          // two accumulators: independent DMMA chains
+        for (; J + 1 < nj; J += 2) {
             const double2 b0 = pB[J * 32], a0 = pA1[J * 32], b1 = pB[J * 32 + 32], a1 = pA1[J * 32 + 32];
-            dmma(acc1, a0.x, b0.x); dmma(acc2, a1.x, b1.x);
-            dmma(acc1, a0.y, b0.y); dmma(acc2, a1.y, b1.y);
+            dmma(acc1, a0.x, b0.x); dmma(e1, a1.x, b1.x);
+            dmma(acc1, a0.y, b0.y); dmma(e1, a1.y, b1.y);
         }
         if (J < nj) dmma2(acc1, pA1[J * 32], pB[J * 32]);
-        acc1.x += acc2.x; acc1.y += acc2.y;
-        finish_tile(p, I, c, acc1, hd);
+        acc1.x += e1.x; acc1.y += e1.y;
+        if (I == c) p.Nd2[(c & 1) * 32] = acc1;
+        else p.tl2[r1 + c * 32] = acc1;
     }
 }
 
@@ -410,7 +420,6 @@ __device__ __forceinline__ void phase_a(const Prob& p, int K, int w, const doubl
 template <int NW, int MINB>
 __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
     extern __shared__ __align__(16) double sm[];
-    int* sidx = reinterpret_cast<int*>(sm);                   // 256 ints
     int* flag = reinterpret_cast<int*>(sm + 128);             // [0] singular
     void* mbar = sm + 130;                                    // mbarrier of the distance-tile bulk copies
     double* tab32 = sm + 136;                                 // 32: 2^(j/32)
@@ -418,6 +427,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
     double2* Nd2 = reinterpret_cast<double2*>(sm + 296);      // 2 x 64: N_diag of column c, double-buffered by c & 1
     double* tiles = sm + KED_HDR;
     constexpr int NT = (NW + 1) * 32;
+    constexpr int NJ = (TWXI_MAX_NNGHS + NT) / NT;            // stations per thread in the B' build
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);    // warp-uniform by construction
@@ -442,83 +452,121 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
     int pend_q = 0, pend_m = 0;
     double pend_yref = 0.0, pend_c00 = 0.0;
 
+    // software pipeline over problems: descriptor two ahead, neighbour indices one ahead
     int slot = blockIdx.x;
-    int2 desc = slot < count ? a.list[start + slot] : make_int2(0, 0);
+    if (slot >= count) return;
+    int2 desc = a.list[start + slot];
+    int2 desc_next = slot + (int)gridDim.x < count ? a.list[start + slot + gridDim.x] : make_int2(0, 0);
+    int sj[NJ], s_first;
+    {
+        const int32_t* ip = a.idx + (size_t)(desc.x / 12) * a.k1;
+        s_first = ip[0];
+#pragma unroll
+        for (int t = 0; t < NJ; ++t) sj[t] = (tid + t * NT < desc.y) ? ip[tid + t * NT] : 0;
+    }
     for (; slot < count; slot += gridDim.x) {
         const int pid = desc.x, n = desc.y;
-        if (slot + (int)gridDim.x < count) desc = a.list[start + slot + gridDim.x];   // prefetch the next descriptor
         const int q = pid / 12, m = pid - q * 12;
         p.n = n;
-        p.hc2 = reinterpret_cast<const double2*>(a.hc + (size_t)(q - a.q0) * a.hc_stride) + lane;
+        const double* hc = a.hc + (size_t)(q - a.q0) * a.hc_stride;
+        p.hc2 = reinterpret_cast<const double2*>(hc) + lane;
         __syncthreads();                                      // previous problem: shared memory fully consumed
         if (tid == 0) {
             flag[0] = 0;
             if (tx_bytes) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_expect_tx(mbar, tx_bytes);
-                const double* src = a.hc + (size_t)(q - a.q0) * a.hc_stride;
                 for (int I = 1; I < NB; ++I)
-                    bulk_g2s(tiles + ltile(I, 0) * 64, src + htile(I, 0) * 64, (uint32_t)I * 512u, mbar);
+                    bulk_g2s(tiles + ltile(I, 0) * 64, hc + htile(I, 0) * 64, (uint32_t)I * 512u, mbar);
             }
         }
-        for (int j = tid; j < n; j += NT) sidx[j] = a.idx[(size_t)q * a.k1 + j];
+        // ---- augmented rows -B' = -[1, dlon, dlat, delev, dlst, y - yref, c0]' into tile row NB: one station per
+        // thread, all its gathers in flight at once (the indices were prefetched during the previous problem)
+        const double* lstm = a.st.lst + (size_t)m * N;
+        const double* normm = a.st.norm + (size_t)m * N;
+        const double yref = normm[s_first];
+        double gl[NJ][6];
+#pragma unroll
+        for (int t = 0; t < NJ; ++t) {
+            const int j = tid + t * NT;
+            if (j < n) {
+                const int s = sj[t];
+                gl[t][0] = a.st.lon[s]; gl[t][1] = a.st.lat[s]; gl[t][2] = a.st.elev[s];
+                gl[t][3] = lstm[s]; gl[t][4] = normm[s]; gl[t][5] = a.h0[(size_t)q * a.k1 + j];
+            }
+        }
         const double* vp = a.vario_is_override ? a.vario + (size_t)q * 3 : a.vario + ((size_t)q * 12 + m) * 3;
         const double nug = vp[0], psill = vp[1], rng = vp[2];
+        const double lon0 = a.qlon[q], lat0 = a.qlat[q], elev0 = a.qelev[q], lst0 = a.qlst[(size_t)q * 12 + m];
+        // raw distances of the diagonal tiles 0, 1 (-> N_diag buffers) and 2 (first look-ahead column)
+        double2 hd = make_double2(0.0, 0.0);
+        if (warp == 0) hd = p.hc2[0];
+        if (warp == 1 && NB > 1) hd = p.hc2[htile(1, 1) * 32];
+        if (warp == NW - 1 && NW > 2 && NB > 2) hd = p.hc2[htile(2, 2) * 32];
         p.cp.c00 = nug + psill;
         p.cp.psill_eff = rng != 0.0 ? psill : 0.0;            // range == 0: pure nugget model (interp.R:223-227)
         p.cp.nir = rng != 0.0 ? -1.0 / rng : 0.0;
-        // raw distances of the diagonal tiles of columns 0 and 1 (consumed after the B' rows are built)
-        const int wd1 = (NB + 1) % (NW + 1);                  // warp that generates tile (1,1) below
-        double2 hd0 = make_double2(0.0, 0.0), hd1 = make_double2(0.0, 0.0);
-        if (warp == 0) hd0 = p.hc2[0];
-        if (warp == wd1 && NB > 1) hd1 = p.hc2[htile(1, 1) * 32];
         if (warp == NW && pending) {
-            ked_finish(a, pend_S, pend_q, pend_m, pend_yref, pend_c00, lane);
+            ked_finish(a.mean, a.var, a.status, pend_S, pend_q, pend_m, pend_yref, pend_c00, lane);
             pending = false;
         }
-        __syncthreads();                                      // sidx visible
-        // augmented rows B' = [1, dlon, dlat, delev, dlst, y - yref, c0]' into tile row NB
         {
-            const double lon0 = a.qlon[q], lat0 = a.qlat[q], elev0 = a.qelev[q], lst0 = a.qlst[(size_t)q * 12 + m];
-            const double* lstm = a.st.lst + (size_t)m * N;
-            const double* normm = a.st.norm + (size_t)m * N;
-            const double yref = normm[sidx[0]];
             double* row = tiles + ltile(NB, 0) * 64;
-            const int cnt = NB * 64;
-            for (int e = tid; e < cnt; e += NT) {
-                const int J = e >> 6, r = (e >> 3) & 7, cidx = e & 7;
-                const int j = 8 * J + cidx;
-                double val = 0.0;
-                if (j < n && r < 7) {
-                    const int s = sidx[j];
-                    if (r == 0) val = 1.0;
-                    else if (r == 1) val = a.st.lon[s] - lon0;
-                    else if (r == 2) val = a.st.lat[s] - lat0;
-                    else if (r == 3) val = (a.st.elev[s] - elev0) * 1e-3;
-                    else if (r == 4) val = (lstm[s] - lst0) * 0.1;
-                    else if (r == 5) val = normm[s] - yref;
-                    else val = cov(a.h0[(size_t)q * a.k1 + j], p.cp, tab32);
+#pragma unroll
+            for (int t = 0; t < NJ; ++t) {
+                const int j = tid + t * NT;
+                if (j < 8 * NB) {
+                    double* col = row + (j >> 3) * 64 + (j & 7);
+                    const bool in = j < n;
+                    col[0] = in ? -1.0 : 0.0;
+                    col[8] = in ? lon0 - gl[t][0] : 0.0;
+                    col[16] = in ? lat0 - gl[t][1] : 0.0;
+                    col[24] = in ? (elev0 - gl[t][2]) * 1e-3 : 0.0;
+                    col[32] = in ? (lst0 - gl[t][3]) * 0.1 : 0.0;
+                    col[40] = in ? yref - gl[t][4] : 0.0;
+                    col[48] = in ? -cov(gl[t][5], p.cp, tab32) : 0.0;
+                    col[56] = 0.0;
                 }
-                row[e] = val;
             }
+        }
+        // prefetch: descriptor two problems ahead, neighbour indices of the next problem
+        desc = desc_next;
+        if (slot + 2 * (int)gridDim.x < count) desc_next = a.list[start + slot + 2 * gridDim.x];
+        if (slot + (int)gridDim.x < count) {
+            const int32_t* ip = a.idx + (size_t)(desc.x / 12) * a.k1;
+            s_first = ip[0];
+#pragma unroll
+            for (int t = 0; t < NJ; ++t) sj[t] = (tid + t * NT < desc.y) ? ip[tid + t * NT] : 0;
         }
         if (tx_bytes) mbar_wait(mbar, parity);                // distance tiles have landed in their slots
         parity ^= 1u;
-        __syncthreads();                                      // B' rows visible
-        // columns 0 and 1 of N (no update terms yet), all warps
+        // ---- covariances in place: slot <- -C(h).  Rows 1..NB-2 need no masking; two tiles per pass
         {
-            const int cnt0 = NB + 1, cnt = cnt0 + NB;         // tiles (I,0), I = 0..NB and (I,1), I = 1..NB
-            for (int it = warp; it < cnt; it += NW + 1) {
-                const int c = it < cnt0 ? 0 : 1;
-                const int I = it < cnt0 ? it : it - cnt0 + 1;
-                finish_tile(p, I, c, make_double2(0.0, 0.0), c == 0 ? hd0 : hd1);
+            const int T0 = NB >= 2 ? ltile(NB - 1, 0) : 0;
+            int t = warp;
+            for (; t + NW + 1 < T0; t += 2 * (NW + 1)) {
+                const double2 h1 = tl2[t * 32], h2 = tl2[(t + NW + 1) * 32];
+                double2 v1, v2;
+                v1.x = -cov(h1.x, p.cp, tab32); v2.x = -cov(h2.x, p.cp, tab32);
+                v1.y = -cov(h1.y, p.cp, tab32); v2.y = -cov(h2.y, p.cp, tab32);
+                tl2[t * 32] = v1; tl2[(t + NW + 1) * 32] = v2;
             }
+            if (t < T0) {
+                const double2 h1 = tl2[t * 32];
+                tl2[t * 32] = make_double2(-cov(h1.x, p.cp, tab32), -cov(h1.y, p.cp, tab32));
+            }
+            const bool plain = 8 * NB <= n;                   // last row of V: identity padding beyond n
+            for (int c = warp; c < NB - 1; c += NW + 1) {
+                const double2 v = cov_tile(tl2[(T0 + c) * 32], 8 * (NB - 1) + p.r8, 8 * c + 2 * p.q4, n, p.cp, tab32, plain);
+                tl2[(T0 + c) * 32] = make_double2(-v.x, -v.y);
+            }
+            if (warp == 0) p.Nd2[0] = neg_cov_diag(p, 0, hd);
+            if (warp == 1) p.Nd2[32] = neg_cov_diag(p, 1, hd);
         }
         __syncthreads();
 
         if (warp == NW) {
             // ================= diagonal warp =====================================================================
-            const double yref = a.st.norm[(size_t)m * N + sidx[0]];
             double2 D = Nd2[lane];
             D.x = -D.x; D.y = -D.y;                           // V_00
             bool singular = false;
@@ -546,11 +594,14 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
             }
         } else {
             // ================= worker warps ======================================================================
-            const int w = warp;
+            const int w = warp, u = NW - 1 - warp;           // phase A / phase B deal rows in opposite orders
             for (int K = 0; K < NB; ++K) {
                 const int c = K + 2;
-                double2 hd = make_double2(0.0, 0.0);
-                if (w == 0 && c < NB) hd = p.hc2[htile(c, c) * 32];           // diagonal distances of column K+2
+                double2 vd = make_double2(0.0, 0.0);
+                if (u == 0) {                                 // -V(c,c) before the barrier, next diagonal tile after it
+                    vd = neg_cov_diag(p, c, hd);
+                    if (c + 1 < NB) hd = p.hc2[htile(c + 1, c + 1) * 32];
+                }
                 named_bar_sync(1, NT);
                 if (flag[0]) break;
                 if (c <= NB) {
@@ -561,19 +612,22 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
                     double2 bK = make_double2(0.0, 0.0);
                     if (K >= 1) bK = tl2[(rb + K - 1) * 32];  // L(K+1,K-1)
                     phase_a<NW>(p, K, w, negW, lk1, bK);
-                    phase_b<NW>(p, c, K, w, hd);
+                    phase_b<NW>(p, c, K, u, vd);
                 }
             }
         }
     }
-    if (warp == NW && pending) ked_finish(a, pend_S, pend_q, pend_m, pend_yref, pend_c00, lane);
+    if (warp == NW && pending) ked_finish(a.mean, a.var, a.status, pend_S, pend_q, pend_m, pend_yref, pend_c00, lane);
 }
 
-// Launch configurations: NW worker warps + the diagonal warp.
+// Launch configurations: NW worker warps + the diagonal warp.  TWXI_KED_CFG="a,b": NB < a -> 3 workers, NB < b -> 5, else 7.
 static int ked_nw_for(int nbv) {
-    static int thr = -1;
-    if (thr < 0) { const char* e = getenv("TWXI_KED_NW7_FROM"); thr = e ? atoi(e) : 13; }
-    return nbv >= thr ? 7 : 3;
+    static int t5 = -1, t7 = -1;
+    if (t5 < 0) {
+        t5 = 13; t7 = 13;
+        if (const char* e = getenv("TWXI_KED_CFG")) sscanf(e, "%d,%d", &t5, &t7);
+    }
+    return nbv < t5 ? 3 : (nbv < t7 ? 5 : 7);
 }
 static size_t ked_smem_for(int nbv) { return (size_t)(KED_HDR + (nbv * (nbv + 1) / 2) * 64) * sizeof(double); }
 
@@ -584,7 +638,7 @@ struct KedWork {                 // device scratch of the kriging stage, owned p
     size_t list_cap = 0;
     int32_t* bins = nullptr;     // bcount | bstart | fill, each KED_MAXNB+1
     int sms = 0;
-    int occ[2][KED_MAXNB + 1];   // resident CTAs per SM for (NW = 3 / 7, size class)
+    int occ[3][KED_MAXNB + 1];   // resident CTAs per SM for (NW = 3 / 5 / 7, size class)
 };
 static thread_local KedWork g_ked;
 constexpr int KED_NBMAX = 21;
@@ -597,14 +651,17 @@ int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
         TWXI_CUDA(cudaGetDeviceProperties(&p, c.device));
         TWXI_CUDA(cudaMalloc((void**)&w.bins, 3 * (KED_MAXNB + 1) * sizeof(int32_t)));
         const int smem_max = (int)ked_smem_for(KED_NBMAX);
-        TWXI_CUDA(cudaFuncSetAttribute(ked_kernel<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-        TWXI_CUDA(cudaFuncSetAttribute(ked_kernel<7, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        TWXI_CUDA(cudaFuncSetAttribute(ked_kernel<3, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        TWXI_CUDA(cudaFuncSetAttribute(ked_kernel<5, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        TWXI_CUDA(cudaFuncSetAttribute(ked_kernel<7, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         for (int nb = 1; nb <= KED_NBMAX; ++nb) {
-            int o3 = 0, o7 = 0;
-            TWXI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, ked_kernel<3, 8>, 128, ked_smem_for(nb)));
-            TWXI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o7, ked_kernel<7, 4>, 256, ked_smem_for(nb)));
+            int o3 = 0, o5 = 0, o7 = 0;
+            TWXI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, ked_kernel<3, 6>, 128, ked_smem_for(nb)));
+            TWXI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o5, ked_kernel<5, 4>, 192, ked_smem_for(nb)));
+            TWXI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o7, ked_kernel<7, 3>, 256, ked_smem_for(nb)));
             w.occ[0][nb] = std::max(1, o3);
-            w.occ[1][nb] = std::max(1, o7);
+            w.occ[1][nb] = std::max(1, o5);
+            w.occ[2][nb] = std::max(1, o7);
         }
         w.sms = p.multiProcessorCount;
     }
@@ -654,11 +711,12 @@ int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
         for (int nbv = nbmax; nbv >= 1; --nbv) {
             a.nbv = nbv;
             const size_t smem = ked_smem_for(nbv);
-            const bool big = ked_nw_for(nbv) == 7;
-            const int occ = w.occ[big ? 1 : 0][nbv];
+            const int nw = ked_nw_for(nbv);
+            const int occ = w.occ[(nw - 3) / 2][nbv];
             const int grid = std::min(w.sms * occ, std::max(1, nt));
-            if (big) ked_kernel<7, 4><<<grid, 256, smem, c.stream>>>(a);
-            else ked_kernel<3, 8><<<grid, 128, smem, c.stream>>>(a);
+            if (nw == 7) ked_kernel<7, 3><<<grid, 256, smem, c.stream>>>(a);
+            else if (nw == 5) ked_kernel<5, 4><<<grid, 192, smem, c.stream>>>(a);
+            else ked_kernel<3, 6><<<grid, 128, smem, c.stream>>>(a);
             TWXI_LAUNCH_CHECK();
         }
     }

@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtwxi.so")
+LIB_PATH = os.environ.get("TWXI_LIB") or os.path.join(HERE, "libtwxi.so")   # TWXI_LIB: instrumented developer builds
 
 MEM_HOST, MEM_DEVICE = 0, 1
 ST_OK, ST_NO_NNGHS, ST_NO_VARIO, ST_TOO_FEW_STNS, ST_SINGULAR, ST_FIXER_EMPTY, ST_CLIMDIV, ST_KNN_TIES = range(8)

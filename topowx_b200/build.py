@@ -32,14 +32,16 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_lib(force=False, verbose=False):
-    if not force and not needs_build():
+def build_lib(force=False, verbose=False, extra=(), out=None, tag=""):  # noqa: C901
+    """extra/out/tag: instrumented developer builds (e.g. extra=["-DTWXI_KED_PROFILE"], out="libtwxi_prof.so")."""
+    target = os.path.join(HERE, out) if out else LIB
+    if not force and target == LIB and not needs_build():
         return LIB
     objs = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(CSRC, src.replace(".cu", tag + ".o"))
+        cmd = [_nvcc()] + NVCC_FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:
@@ -48,10 +50,13 @@ def build_lib(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed on %s" % src)
-    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart"]
+    cmd = [_nvcc(), "-shared", "-o", target] + objs + ["-lcudart"]
     subprocess.check_call(cmd)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":
-    print(build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--prof" in sys.argv:
+        print(build_lib(force=True, extra=["-DTWXI_KED_PROFILE"], out="libtwxi_prof.so", tag="_prof"))
+    else:
+        print(build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -42,7 +42,7 @@
 
 namespace twxi {
 
-constexpr int KED_HDR = 128 + 8 + 32 + 2 * 128;   // doubles: neighbour indices (256 ints), flag + mbarrier, 2^(j/32), -inv(L_KK) x2, N_diag x2
+constexpr int KED_HDR = 8 + 32 + 2 * 128;         // doubles: flag + mbarrier, 2^(j/32), -inv(L_KK) x2, N_diag x2
 constexpr int KED_MAXNB = 32;           // size classes NBv = 1..32 (n <= 255)
 
 struct KedArgs {
@@ -417,14 +417,23 @@ __device__ __forceinline__ void phase_a(const Prob& p, int K, int w, const doubl
     }
 }
 
+#ifdef TWXI_KED_PROFILE
+__device__ unsigned long long g_ked_prof[16];
+#define KPROF(i, v) do { if (lane == 0) atomicAdd(&g_ked_prof[i], (unsigned long long)(v)); } while (0)
+#define KCLK() clock64()
+#else
+#define KPROF(i, v) do { } while (0)
+#define KCLK() 0ll
+#endif
+
 template <int NW, int MINB>
 __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
     extern __shared__ __align__(16) double sm[];
-    int* flag = reinterpret_cast<int*>(sm + 128);             // [0] singular
-    void* mbar = sm + 130;                                    // mbarrier of the distance-tile bulk copies
-    double* tab32 = sm + 136;                                 // 32: 2^(j/32)
-    double2* Wt2 = reinterpret_cast<double2*>(sm + 168);      // 2 x 64: -inv(L_KK), double-buffered by K & 1
-    double2* Nd2 = reinterpret_cast<double2*>(sm + 296);      // 2 x 64: N_diag of column c, double-buffered by c & 1
+    int* flag = reinterpret_cast<int*>(sm);                   // [0] singular
+    void* mbar = sm + 2;                                      // mbarrier of the distance-tile bulk copies
+    double* tab32 = sm + 8;                                   // 32: 2^(j/32)
+    double2* Wt2 = reinterpret_cast<double2*>(sm + 40);       // 2 x 64: -inv(L_KK), double-buffered by K & 1
+    double2* Nd2 = reinterpret_cast<double2*>(sm + 168);      // 2 x 64: N_diag of column c, double-buffered by c & 1
     double* tiles = sm + KED_HDR;
     constexpr int NT = (NW + 1) * 32;
     constexpr int NJ = (TWXI_MAX_NNGHS + NT) / NT;            // stations per thread in the B' build
@@ -470,7 +479,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
         p.n = n;
         const double* hc = a.hc + (size_t)(q - a.q0) * a.hc_stride;
         p.hc2 = reinterpret_cast<const double2*>(hc) + lane;
+        const long long tp0 = KCLK();
         __syncthreads();                                      // previous problem: shared memory fully consumed
+        const long long tp1 = KCLK();
         if (tid == 0) {
             flag[0] = 0;
             if (tx_bytes) {
@@ -538,20 +549,23 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
 #pragma unroll
             for (int t = 0; t < NJ; ++t) sj[t] = (tid + t * NT < desc.y) ? ip[tid + t * NT] : 0;
         }
+        const long long tp2 = KCLK();
         if (tx_bytes) mbar_wait(mbar, parity);                // distance tiles have landed in their slots
         parity ^= 1u;
+        const long long tp3 = KCLK();
         // ---- covariances in place: slot <- -C(h).  Rows 1..NB-2 need no masking; two tiles per pass
         {
             const int T0 = NB >= 2 ? ltile(NB - 1, 0) : 0;
+            constexpr int NWT = NW + 1;
             int t = warp;
-            for (; t + NW + 1 < T0; t += 2 * (NW + 1)) {
-                const double2 h1 = tl2[t * 32], h2 = tl2[(t + NW + 1) * 32];
-                double2 v1, v2;
-                v1.x = -cov(h1.x, p.cp, tab32); v2.x = -cov(h2.x, p.cp, tab32);
-                v1.y = -cov(h1.y, p.cp, tab32); v2.y = -cov(h2.y, p.cp, tab32);
-                tl2[t * 32] = v1; tl2[(t + NW + 1) * 32] = v2;
+            for (; t + 3 * NWT < T0; t += 4 * NWT) {
+                const double2 h1 = tl2[t * 32], h2 = tl2[(t + NWT) * 32], h3 = tl2[(t + 2 * NWT) * 32], h4 = tl2[(t + 3 * NWT) * 32];
+                double2 v1, v2, v3, v4;
+                v1.x = -cov(h1.x, p.cp, tab32); v2.x = -cov(h2.x, p.cp, tab32); v3.x = -cov(h3.x, p.cp, tab32); v4.x = -cov(h4.x, p.cp, tab32);
+                v1.y = -cov(h1.y, p.cp, tab32); v2.y = -cov(h2.y, p.cp, tab32); v3.y = -cov(h3.y, p.cp, tab32); v4.y = -cov(h4.y, p.cp, tab32);
+                tl2[t * 32] = v1; tl2[(t + NWT) * 32] = v2; tl2[(t + 2 * NWT) * 32] = v3; tl2[(t + 3 * NWT) * 32] = v4;
             }
-            if (t < T0) {
+            for (; t < T0; t += NWT) {
                 const double2 h1 = tl2[t * 32];
                 tl2[t * 32] = make_double2(-cov(h1.x, p.cp, tab32), -cov(h1.y, p.cp, tab32));
             }
@@ -563,7 +577,13 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
             if (warp == 0) p.Nd2[0] = neg_cov_diag(p, 0, hd);
             if (warp == 1) p.Nd2[32] = neg_cov_diag(p, 1, hd);
         }
+        const long long tp4 = KCLK();
         __syncthreads();
+        const long long tp5 = KCLK();
+        if (warp == NW) { KPROF(0, 1); KPROF(1, tp5 - tp0); KPROF(2, tp2 - tp1); KPROF(3, tp4 - tp3); }
+        if (warp == 0) KPROF(8, 1);
+        long long t_bar = 0, t_x = 0, t_y = 0;
+        (void)tp1; (void)tp2; (void)tp3; (void)tp4; (void)t_x; (void)t_y;
 
         if (warp == NW) {
             // ================= diagonal warp =====================================================================
@@ -572,11 +592,16 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
             bool singular = false;
             for (int K = 0; K < NB; ++K) {
                 double2 w;
+                const long long tc0 = KCLK();
                 const bool ok = chol8_inverse(D, w, lane);
                 w.x = -w.x; w.y = -w.y;
+                t_x += KCLK() - tc0;
                 Wt2[(K & 1) * 32 + lane] = w;
                 if (!ok && lane == 0) flag[0] = 1;
+                const long long tb0 = KCLK();
                 named_bar_sync(1, NT);                        // -inv(L_KK) published; the workers' stage K-1 is complete
+                const long long tb1 = KCLK();
+                t_bar += tb1 - tb0;
                 if (flag[0]) { singular = true; break; }
                 const int rb = ltile(K + 1, 0);
                 double2 l = make_double2(0.0, 0.0);
@@ -585,7 +610,12 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
                 if (K >= 1) { const double2 t = tl2[(rb + K - 1) * 32]; dmma2(nd, t, t); }
                 dmma2(nd, l, l);
                 D.x = -nd.x; D.y = -nd.y;                     // D_{K+1}; for K+1 == NB this is -S
+#ifdef TWXI_KED_PROFILE
+                if (__double_as_longlong(D.x) == 0x7ff8dead00000000ll) flag[0] = 2;    // keep D live before the clock read
+#endif
+                t_y += KCLK() - tb1;
             }
+            KPROF(4, KCLK() - tp5); KPROF(5, t_bar); KPROF(6, t_x); KPROF(7, t_y);
             if (singular) {
                 if (lane == 0) atomicCAS(a.status + q, TWXI_ST_OK, TWXI_ST_SINGULAR);
             } else {
@@ -602,7 +632,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
                     vd = neg_cov_diag(p, c, hd);
                     if (c + 1 < NB) hd = p.hc2[htile(c + 1, c + 1) * 32];
                 }
+                const long long tb0 = KCLK();
                 named_bar_sync(1, NT);
+                const long long tb1 = KCLK();
+                t_bar += tb1 - tb0;
                 if (flag[0]) break;
                 if (c <= NB) {
                     const double2 negW = Wt2[(K & 1) * 32 + lane];
@@ -612,9 +645,13 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
                     double2 bK = make_double2(0.0, 0.0);
                     if (K >= 1) bK = tl2[(rb + K - 1) * 32];  // L(K+1,K-1)
                     phase_a<NW>(p, K, w, negW, lk1, bK);
+                    const long long ta1 = KCLK();
+                    t_x += ta1 - tb1;
                     phase_b<NW>(p, c, K, u, vd);
+                    t_y += KCLK() - ta1;
                 }
             }
+            if (warp == 0) { KPROF(9, KCLK() - tp5); KPROF(10, t_bar); KPROF(11, t_x); KPROF(12, t_y); }
         }
     }
     if (warp == NW && pending) ked_finish(a.mean, a.var, a.status, pend_S, pend_q, pend_m, pend_yref, pend_c00, lane);
@@ -638,10 +675,19 @@ struct KedWork {                 // device scratch of the kriging stage, owned p
     size_t list_cap = 0;
     int32_t* bins = nullptr;     // bcount | bstart | fill, each KED_MAXNB+1
     int sms = 0;
-    int occ[3][KED_MAXNB + 1];   // resident CTAs per SM for (NW = 3 / 5 / 7, size class)
+    int occ[4][KED_MAXNB + 1];   // resident CTAs per SM for (NW = 3 / 5 / 7 / 3 with 64 registers, size class)
 };
 static thread_local KedWork g_ked;
 constexpr int KED_NBMAX = 21;
+
+#ifdef TWXI_KED_PROFILE
+extern "C" int twxi_ked_prof(unsigned long long* out16, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, g_ked_prof, sizeof(g_ked_prof));
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_ked_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
     if (b.npts <= 0) return TWXI_OK;
@@ -652,10 +698,13 @@ int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
         TWXI_CUDA(cudaMalloc((void**)&w.bins, 3 * (KED_MAXNB + 1) * sizeof(int32_t)));
         const int smem_max = (int)ked_smem_for(KED_NBMAX);
         TWXI_CUDA(cudaFuncSetAttribute(ked_kernel<3, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        TWXI_CUDA(cudaFuncSetAttribute(ked_kernel<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         TWXI_CUDA(cudaFuncSetAttribute(ked_kernel<5, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         TWXI_CUDA(cudaFuncSetAttribute(ked_kernel<7, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         for (int nb = 1; nb <= KED_NBMAX; ++nb) {
-            int o3 = 0, o5 = 0, o7 = 0;
+            int o3 = 0, o5 = 0, o7 = 0, o38 = 0;
+            TWXI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o38, ked_kernel<3, 8>, 128, ked_smem_for(nb)));
+            w.occ[3][nb] = std::max(1, o38);
             TWXI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, ked_kernel<3, 6>, 128, ked_smem_for(nb)));
             TWXI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o5, ked_kernel<5, 4>, 192, ked_smem_for(nb)));
             TWXI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o7, ked_kernel<7, 3>, 256, ked_smem_for(nb)));
@@ -712,9 +761,11 @@ int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
             a.nbv = nbv;
             const size_t smem = ked_smem_for(nbv);
             const int nw = ked_nw_for(nbv);
-            const int occ = w.occ[(nw - 3) / 2][nbv];
+            const bool small = nw == 3 && w.occ[3][nbv] > w.occ[0][nbv];      // shared memory leaves room for > 6 CTAs
+            const int occ = small ? w.occ[3][nbv] : w.occ[(nw - 3) / 2][nbv];
             const int grid = std::min(w.sms * occ, std::max(1, nt));
-            if (nw == 7) ked_kernel<7, 3><<<grid, 256, smem, c.stream>>>(a);
+            if (small) ked_kernel<3, 8><<<grid, 128, smem, c.stream>>>(a);
+            else if (nw == 7) ked_kernel<7, 3><<<grid, 256, smem, c.stream>>>(a);
             else if (nw == 5) ked_kernel<5, 4><<<grid, 192, smem, c.stream>>>(a);
             else ked_kernel<3, 6><<<grid, 128, smem, c.stream>>>(a);
             TWXI_LAUNCH_CHECK();

@@ -37,10 +37,18 @@
 //     only synchronisation is one bar.sync per block column.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <algorithm>
 #include "twxi_internal.cuh"
 
 namespace twxi {
+
+#ifndef TWXI_KED_FAKE
+#define TWXI_KED_FAKE 0          // timing experiments only (results are wrong when non-zero)
+#endif
+#ifndef TWXI_KED_PAIR
+#define TWXI_KED_PAIR 1          // workers update two tile rows per pass (four independent DMMA chains)
+#endif
 
 constexpr int KED_HDR = 8 + 32 + 2 * 128;         // doubles: flag + mbarrier, 2^(j/32), -inv(L_KK) x2, N_diag x2
 constexpr int KED_MAXNB = 32;           // size classes NBv = 1..32 (n <= 255)
@@ -128,6 +136,83 @@ __device__ __forceinline__ bool chol8_inverse(double2 a, double2& w, int lane) {
     return ok;
 }
 
+// 1/sqrt(d) for a normal positive double: MUFU seed and one third-order step (error ~ e^3), like fast_rcp.
+__device__ __forceinline__ double fast_rsqrt(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double e = fma(-d * y, y, 1.0);
+    const double g = fma(e, 0.375, 0.5) * e;
+    return fma(y, g, y);
+}
+
+// Tensor-pipe form of the pivot-tile factorisation.  With the tile in C-fragment layout, lane (r, q = k/2) owns
+// M[r][k]; feeding that column (zero in the other lanes) as BOTH operands of one DMMA adds the outer product
+// M[:,k] M[:,k]' to every element at once: no column broadcasts and no predicates (finished rows and columns are exactly
+// zero and stay zero).  Fraction-free (Bareiss) scaling keeps the reciprocal off the serial pivot chain:
+//     M <- (d_k M - M[:,k] M[:,k]') / M(k-1)_(k-1,k-1),   d_k := M(k)_kk  (pivot of LDL' = d_k / previous d).
+// The inverse is accumulated TRANSPOSED, Z = inv(L)': Z[c][r] -= Z[c][k] m_rk needs column k of Z and the multipliers
+// m_rk = M[r][k] / d_k, both already sitting in the lanes (r, q = k/2) that feed the DMMA — no shuffles either.
+// Per pivot: one shuffle (d_k), two DMMAs, ~8 scalar FP64 ops; chain = shuffle + DMUL + DMMA.  The update of Z for
+// pivot k-1 is issued after the shuffle of pivot k so that it runs in the shuffle's shadow (in-order issue).
+// Returns Z scaled by the inverse square roots of the pivots (columns), i.e. the transpose of inv(chol(A)).
+template <int NPIV>
+__device__ __forceinline__ bool elim8_mma(double2& a, int lane) {
+    const int q = lane & 3;
+    bool ok = true;
+    double rprev = 1.0;                                       // 1 / d_(k-1)
+#pragma unroll
+    for (int k = 0; k < NPIV; ++k) {
+        const int kq = k >> 1;
+        const double mine = (k & 1) ? a.y : a.x;
+        const double e = (q == kq) ? mine : 0.0;              // M[r][k] in the lanes that own column k
+        const double dk = __shfl_sync(0xffffffffu, mine, 4 * k + kq);
+        const double ax = a.x * rprev, ay = a.y * rprev;      // in the shadow of the shuffle
+        ok = ok && (dk > 0.0);
+        const double es = -e * rprev;
+        double2 c = make_double2(dk * ax, dk * ay);           // M <- (d_k M - M[:,k] M[:,k]') / previous pivot
+        dmma(c, es, e);
+        a = c;
+        rprev = fast_rcp(dk);
+    }
+    a.x *= rprev; a.y *= rprev;                               // Schur complement of the first NPIV pivots
+    return ok;
+}
+
+// Returns Z = transpose of inv(chol(A)) in C-fragment layout (A = the SPD tile `a`).  The seven Z updates depend on
+// each other only through Z, so the scheduler is free to run them behind the pivot chain.
+__device__ __forceinline__ bool chol8_inverse_t(double2 a, double2& z, int lane) {
+    const int r = lane >> 2, q = lane & 3;
+    z.x = (2 * q == r) ? 1.0 : 0.0;
+    z.y = (2 * q + 1 == r) ? 1.0 : 0.0;
+    bool ok = true;
+    double dx = 1.0, dy = 1.0;                                // LDL' pivots of columns 2q, 2q+1 (scale the columns of Z)
+    double rprev = 1.0;                                       // 1 / d_(k-1)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int kq = k >> 1;
+        const double mine = (k & 1) ? a.y : a.x;
+        const double e = (q == kq) ? mine : 0.0;              // M[r][k] in the lanes that own column k
+        const double dk = __shfl_sync(0xffffffffu, mine, 4 * k + kq);
+        const double ax = a.x * rprev, ay = a.y * rprev;      // in the shadow of the shuffle
+        ok = ok && (dk > 0.0);
+        const double piv = dk * rprev;
+        if (kq == q) { if (k & 1) dy = piv; else dx = piv; }
+        if (k < 7) {
+            const double es = -e * rprev;
+            double2 c = make_double2(dk * ax, dk * ay);       // M <- (d_k M - M[:,k] M[:,k]') / previous pivot
+            dmma(c, es, e);
+            a = c;
+            const double p = fast_rcp(dk);
+            const double mneg = (r == k) ? 0.0 : -e * p;      // Z[c][r] -= Z[c][k] m_rk
+            dmma(z, (k & 1) ? z.y : z.x, mneg);
+            rprev = p;
+        }
+    }
+    z.x *= fast_rsqrt(dx);
+    z.y *= fast_rsqrt(dy);
+    return ok;
+}
+
 // ---- 1. compact distance tiles -------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) hgather_kernel(StnTable st, int q0, int nq, int k1, const int32_t* idx,
                                                       const int32_t* nn, const int32_t* status, double* hc,
@@ -149,7 +234,7 @@ __global__ void __launch_bounds__(256) hgather_kernel(StnTable st, int q0, int n
         for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
             const int i = 8 * I + ((e >> 3) & 7), j = 8 * (e >> 6) + (e & 7);
             double h = 0.0;
-            if (i < nmax && j < i) h = st.H[(size_t)sidx[i] * N + sidx[j]];
+            if (i < nmax && j < nmax && j != i) h = st.H[(size_t)sidx[i] * N + sidx[j]];   // diagonal tiles: both triangles
             row[e] = h;
         }
     }
@@ -212,7 +297,11 @@ struct CovPar {
 };
 // C(h) of an off-diagonal pair: nug+psill at h == 0 (co-located stations -> singular, as in gstat)
 __device__ __forceinline__ double cov(double h, const CovPar& cp, const double* tab32) {
+#if TWXI_KED_FAKE == 2
+    const double e = cp.psill_eff * (h * cp.nir);
+#else
     const double e = cp.psill_eff * exp_neg(h * cp.nir, tab32);
+#endif
     return h == 0.0 ? cp.c00 : e;
 }
 // V tile (I, K) from its distance tile in C-fragment layout; lane holds (i, j) and (i, j+1).
@@ -222,10 +311,11 @@ __device__ __forceinline__ double2 cov_tile(double2 h, int i, int j, int n, cons
     double2 v;
     v.x = cov(h.x, cp, tab32);
     v.y = cov(h.y, cp, tab32);
-    if (!plain) {
-        if (j >= i) v.x = (j == i) ? cp.c00 : 0.0;            // diagonal / upper part of a diagonal tile
-        if (j + 1 >= i) v.y = (j + 1 == i) ? cp.c00 : 0.0;
-        if (i >= n) { v.x = (i == j) ? 1.0 : 0.0; v.y = (i == j + 1) ? 1.0 : 0.0; }   // identity padding
+    if (!plain) {                                             // diagonal tiles are kept fully symmetric (elim8_mma)
+        if (j == i) v.x = cp.c00;
+        if (j + 1 == i) v.y = cp.c00;
+        if (i >= n || j >= n) v.x = (i == j) ? 1.0 : 0.0;     // identity padding
+        if (i >= n || j + 1 >= n) v.y = (i == j + 1) ? 1.0 : 0.0;
     }
     return v;
 }
@@ -254,63 +344,26 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
 }
 
-// 5x5 GLS from S = B'V^-1B held by one warp in C-fragment layout: mean and variance of the kriging predictor
-__device__ __noinline__ void ked_finish(double* mean_out, double* var_out, int32_t* status, double2 s0, int q, int m, double yref, double c00, int lane) {
-    double S[7][7];
-#pragma unroll
-    for (int r = 0; r < 7; ++r)
-#pragma unroll
-        for (int cc = 0; cc <= r; ++cc)
-            S[r][cc] = __shfl_sync(0xffffffffu, (cc & 1) ? s0.y : s0.x, 4 * r + (cc >> 1));
-    if (lane != 0) return;
-    double G[5][5], gy[5], rr[5], t[5], dinv[5];
-    bool ok = true;
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-#pragma unroll
-        for (int j = 0; j <= i; ++j) G[i][j] = S[i][j];
-        gy[i] = S[5][i];
-        rr[i] = (i == 0 ? 1.0 : 0.0) - S[6][i];
-    }
-    const double scy = S[6][5], scc = S[6][6];
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-        double d = G[j][j];
-#pragma unroll
-        for (int k = 0; k < j; ++k) d = fma(-G[j][k], G[j][k], d);
-        ok = ok && (d > 0.0);
-        const double ri = rsqrt(d);
-        dinv[j] = ri;
-#pragma unroll
-        for (int i = j + 1; i < 5; ++i) {
-            double sacc = G[i][j];
-#pragma unroll
-            for (int k = 0; k < j; ++k) sacc = fma(-G[i][k], G[j][k], sacc);
-            G[i][j] = sacc * ri;
+// 5x5 GLS from S = B'V^-1B held by one warp in C-fragment layout: mean and variance of the kriging predictor.
+// S = [[G, g_y, g_c], [., ., s_cy], [., ., s_cc]] (row/column 7 are padding).  Bordering G with g_y and -(x0 - g_c)
+// (x0 = e_0: the drift columns are centred on the prediction point) and eliminating its 5 pivots leaves
+//     T[5][6] = s_cy + g_y' G^-1 (x0 - g_c) = mean - yref,     T[6][6] = -(x0 - g_c)' G^-1 (x0 - g_c),
+// so var = C(0) - s_cc - T[6][6].  The elimination runs on the tensor pipe like the pivot tiles (elim8_mma).
+__device__ __forceinline__ void ked_finish(double* mean_out, double* var_out, int32_t* status, double2 s0, int q, int m,
+                                           double yref, double c00, int lane) {
+    const double scc = s0.x;                                  // S[6][6] in lane 27
+    if (lane == 4 * 6 + 0 || lane == 4 * 0 + 3) s0.x -= 1.0;  // (6,0) and (0,6): g_c - x0
+    if (lane == 4 * 6 + 3) s0.x = 0.0;                        // (6,6)
+    const bool ok = elim8_mma<5>(s0, lane);
+    const double t56 = __shfl_sync(0xffffffffu, s0.x, 4 * 5 + 3);
+    if (lane == 4 * 6 + 3) {
+        const double mean = t56 + yref, var = c00 - scc - s0.x;
+        if (!ok || !isfinite(mean) || !isfinite(var)) {
+            atomicCAS(status + q, TWXI_ST_OK, TWXI_ST_SINGULAR);
+        } else {
+            mean_out[(size_t)q * 12 + m] = mean;
+            var_out[(size_t)q * 12 + m] = var;
         }
-    }
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {                            // L u = r
-        double sacc = rr[i];
-#pragma unroll
-        for (int k = 0; k < i; ++k) sacc = fma(-G[i][k], t[k], sacc);
-        t[i] = sacc * dinv[i];
-    }
-#pragma unroll
-    for (int i = 4; i >= 0; --i) {                           // L' t = u
-        double sacc = t[i];
-#pragma unroll
-        for (int k = i + 1; k < 5; ++k) sacc = fma(-G[k][i], t[k], sacc);
-        t[i] = sacc * dinv[i];
-    }
-    double mean = scy + yref, var = c00 - scc;
-#pragma unroll
-    for (int i = 0; i < 5; ++i) { mean = fma(t[i], gy[i], mean); var = fma(rr[i], t[i], var); }
-    if (!ok || !isfinite(mean) || !isfinite(var)) {
-        atomicCAS(status + q, TWXI_ST_OK, TWXI_ST_SINGULAR);
-    } else {
-        mean_out[(size_t)q * 12 + m] = mean;
-        var_out[(size_t)q * 12 + m] = var;
     }
 }
 
@@ -331,89 +384,84 @@ __device__ __forceinline__ double2 neg_cov_diag(const Prob& p, int c, double2 hd
     return make_double2(-v.x, -v.y);
 }
 
-// Look-ahead: N(I,c) += sum_{J<nj} L(I,J) L(c,J)' for rows I = c + u, c + u + NW, ... (two rows per pass, even and
-// odd J in separate accumulators: four independent DMMA chains).  The slots already hold -V(I,c) (or -B'); the
-// diagonal tile (I == c) starts from `vd` and goes to the N_diag buffer.
+// Stage K of a worker (rows I = K+2+u, K+2+u+NW, ..., two rows per pass: four independent DMMA chains):
+//   L(I,K)   = N(I,K) (-W)'                                          panel solve, stored in place
+//   N(I,K+1) += sum_{J<K} L(I,J) L(K+1,J)' + L(I,K) L(K+1,K)'        column K+1 is complete after this stage
+// and, by the owner of row K+2 (u == 0), the next-but-one pivot tile
+//   N_diag(K+2) = -V(K+2,K+2) + sum_{J<=K} L(K+2,J) L(K+2,J)'.
+// Every tile of the strict lower triangle is read and written exactly twice (update, then solve).
 template <int NW>
-__device__ __forceinline__ void phase_b(const Prob& p, int c, int nj, int u, double2 vd) {
-    const double2* pB = p.tl2 + ltile(c, 0) * 32;
+__device__ __forceinline__ void stage_rows(const Prob& p, int K, int u, const double2 negW, const double2 lk1, double2 vd) {
+    double2* tl2 = p.tl2;
+    const double2* pB = tl2 + ltile(K + 1, 0) * 32;           // row K+1: L(K+1, J), J < K
+    const int c = K + 2;
     int I = c + u;
-    for (; I + NW <= p.NB; I += 2 * NW) {
+    double2 lfirst = make_double2(0.0, 0.0);                  // L(K+2,K) of the u == 0 worker
+    for (; TWXI_KED_PAIR && I + NW <= p.NB; I += 2 * NW) {
         const int r1 = ltile(I, 0) * 32, r2 = ltile(I + NW, 0) * 32;
-        const double2* pA1 = p.tl2 + r1;
-        const double2* pA2 = p.tl2 + r2;
-        double2 acc1 = (I == c) ? vd : p.tl2[r1 + c * 32];
-        double2 acc2 = p.tl2[r2 + c * 32];
+        const double2* pA1 = tl2 + r1;
+        const double2* pA2 = tl2 + r2;
+        const double2 n1 = pA1[K * 32], n2 = pA2[K * 32];
+        double2 acc1 = pA1[K * 32 + 32], acc2 = pA2[K * 32 + 32];
+        double2 l1 = make_double2(0.0, 0.0), l2 = make_double2(0.0, 0.0);
+        dmma(l1, n1.x, negW.x); dmma(l2, n2.x, negW.x);
+        dmma(l1, n1.y, negW.y); dmma(l2, n2.y, negW.y);
         double2 e1 = make_double2(0.0, 0.0), e2 = make_double2(0.0, 0.0);
         int J = 0;
-        for (; J + 1 < nj; J += 2) {
+        for (; J + 1 < K; J += 2) {
             const double2 b0 = pB[J * 32], b1 = pB[J * 32 + 32];
             const double2 a10 = pA1[J * 32], a11 = pA1[J * 32 + 32];
             const double2 a20 = pA2[J * 32], a21 = pA2[J * 32 + 32];
             dmma(acc1, a10.x, b0.x); dmma(acc2, a20.x, b0.x); dmma(e1, a11.x, b1.x); dmma(e2, a21.x, b1.x);
             dmma(acc1, a10.y, b0.y); dmma(acc2, a20.y, b0.y); dmma(e1, a11.y, b1.y); dmma(e2, a21.y, b1.y);
         }
-        if (J < nj) {
+        if (J < K) {
             const double2 b0 = pB[J * 32], a10 = pA1[J * 32], a20 = pA2[J * 32];
             dmma(acc1, a10.x, b0.x); dmma(acc2, a20.x, b0.x);
             dmma(acc1, a10.y, b0.y); dmma(acc2, a20.y, b0.y);
         }
+        tl2[r1 + K * 32] = l1; tl2[r2 + K * 32] = l2;
+        dmma(e1, l1.x, lk1.x); dmma(e2, l2.x, lk1.x);
+        dmma(e1, l1.y, lk1.y); dmma(e2, l2.y, lk1.y);
         acc1.x += e1.x; acc1.y += e1.y; acc2.x += e2.x; acc2.y += e2.y;
-        if (I == c) p.Nd2[(c & 1) * 32] = acc1;
-        else p.tl2[r1 + c * 32] = acc1;
-        p.tl2[r2 + c * 32] = acc2;
+        tl2[r1 + K * 32 + 32] = acc1; tl2[r2 + K * 32 + 32] = acc2;
+        if (I == c) lfirst = l1;
     }
-    if (I <= p.NB) {
+    for (; I <= p.NB; I += NW) {
         const int r1 = ltile(I, 0) * 32;
-        const double2* pA1 = p.tl2 + r1;
-        double2 acc1 = (I == c) ? vd : p.tl2[r1 + c * 32];
+        const double2* pA1 = tl2 + r1;
+        const double2 n1 = pA1[K * 32];
+        double2 acc1 = make_double2(0.0, 0.0);
+        if (I > K + 1) acc1 = pA1[K * 32 + 32];
+        double2 l1 = make_double2(0.0, 0.0);
+        dmma2(l1, n1, negW);
         double2 e1 = make_double2(0.0, 0.0);
         int J = 0;
-        for (; J + 1 < nj; J += 2) {
+        for (; J + 1 < K; J += 2) {
             const double2 b0 = pB[J * 32], a0 = pA1[J * 32], b1 = pB[J * 32 + 32], a1 = pA1[J * 32 + 32];
             dmma(acc1, a0.x, b0.x); dmma(e1, a1.x, b1.x);
             dmma(acc1, a0.y, b0.y); dmma(e1, a1.y, b1.y);
         }
-        if (J < nj) dmma2(acc1, pA1[J * 32], pB[J * 32]);
+        if (J < K) dmma2(acc1, pA1[J * 32], pB[J * 32]);
+        tl2[r1 + K * 32] = l1;
+        dmma2(e1, l1, lk1);
         acc1.x += e1.x; acc1.y += e1.y;
-        if (I == c) p.Nd2[(c & 1) * 32] = acc1;
-        else p.tl2[r1 + c * 32] = acc1;
+        tl2[r1 + K * 32 + 32] = acc1;
+        if (I == c) lfirst = l1;
     }
-}
-
-// Panel solve of column K and the last two updates of column K+1 for rows K+2+w, K+2+w+NW, ...
-//   L(I,K) = N(I,K) (-W)';  N(I,K+1) += L(I,K-1) L(K+1,K-1)' + L(I,K) L(K+1,K)'
-template <int NW>
-__device__ __forceinline__ void phase_a(const Prob& p, int K, int w, const double2 negW, const double2 lk1, const double2 bK) {
-    double2* tl2 = p.tl2;
-    int I = K + 2 + w;
-    for (; I + NW <= p.NB; I += 2 * NW) {
-        const int s1 = (ltile(I, 0) + K) * 32, s2 = (ltile(I + NW, 0) + K) * 32;
-        const double2 n1 = tl2[s1], n2 = tl2[s2];
-        double2 c1 = tl2[s1 + 32], c2 = tl2[s2 + 32];
-        double2 l1 = make_double2(0.0, 0.0), l2 = make_double2(0.0, 0.0);
-        dmma(l1, n1.x, negW.x); dmma(l2, n2.x, negW.x);
-        dmma(l1, n1.y, negW.y); dmma(l2, n2.y, negW.y);
-        if (K >= 1) {
-            const double2 a1 = tl2[s1 - 32], a2 = tl2[s2 - 32];
-            dmma(c1, a1.x, bK.x); dmma(c2, a2.x, bK.x);
-            dmma(c1, a1.y, bK.y); dmma(c2, a2.y, bK.y);
+    if (u == 0 && c <= p.NB) {                                // pivot tile of stage K+2 (the S tile for c == NB)
+        const double2* pA = tl2 + ltile(c, 0) * 32;
+        double2 acc = vd, e = make_double2(0.0, 0.0);
+        int J = 0;
+        for (; J + 1 < K; J += 2) {
+            const double2 a0 = pA[J * 32], a1 = pA[J * 32 + 32];
+            dmma(acc, a0.x, a0.x); dmma(e, a1.x, a1.x);
+            dmma(acc, a0.y, a0.y); dmma(e, a1.y, a1.y);
         }
-        tl2[s1] = l1; tl2[s2] = l2;
-        dmma(c1, l1.x, lk1.x); dmma(c2, l2.x, lk1.x);
-        dmma(c1, l1.y, lk1.y); dmma(c2, l2.y, lk1.y);
-        tl2[s1 + 32] = c1; tl2[s2 + 32] = c2;
-    }
-    if (I <= p.NB) {
-        const int s1 = (ltile(I, 0) + K) * 32;
-        const double2 n1 = tl2[s1];
-        double2 c1 = tl2[s1 + 32];
-        double2 l1 = make_double2(0.0, 0.0);
-        dmma2(l1, n1, negW);
-        if (K >= 1) dmma2(c1, tl2[s1 - 32], bK);
-        tl2[s1] = l1;
-        dmma2(c1, l1, lk1);
-        tl2[s1 + 32] = c1;
+        if (J < K) { const double2 a0 = pA[J * 32]; dmma2(acc, a0, a0); }
+        dmma2(e, lfirst, lfirst);
+        acc.x += e.x; acc.y += e.y;
+        p.Nd2[(c & 1) * 32] = acc;
     }
 }
 
@@ -426,7 +474,7 @@ __device__ unsigned long long g_ked_prof[16];
 #define KCLK() 0ll
 #endif
 
-template <int NW, int MINB>
+template <int NW, int MINB, int NMAX>
 __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
     extern __shared__ __align__(16) double sm[];
     int* flag = reinterpret_cast<int*>(sm);                   // [0] singular
@@ -436,7 +484,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
     double2* Nd2 = reinterpret_cast<double2*>(sm + 168);      // 2 x 64: N_diag of column c, double-buffered by c & 1
     double* tiles = sm + KED_HDR;
     constexpr int NT = (NW + 1) * 32;
-    constexpr int NJ = (TWXI_MAX_NNGHS + NT) / NT;            // stations per thread in the B' build
+    constexpr int NJ = (NMAX + NT - 1) / NT;                  // stations per thread in the B' build (n <= NMAX)
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);    // warp-uniform by construction
@@ -510,10 +558,12 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
         const double nug = vp[0], psill = vp[1], rng = vp[2];
         const double lon0 = a.qlon[q], lat0 = a.qlat[q], elev0 = a.qelev[q], lst0 = a.qlst[(size_t)q * 12 + m];
         // raw distances of the diagonal tiles 0, 1 (-> N_diag buffers) and 2 (first look-ahead column)
-        double2 hd = make_double2(0.0, 0.0);
-        if (warp == 0) hd = p.hc2[0];
-        if (warp == 1 && NB > 1) hd = p.hc2[htile(1, 1) * 32];
-        if (warp == NW - 1 && NW > 2 && NB > 2) hd = p.hc2[htile(2, 2) * 32];
+        double2 hd = make_double2(0.0, 0.0), hd1 = make_double2(0.0, 0.0);
+        if (warp == NW) {                                     // the diagonal warp owns V(0,0) and V(1,1)
+            hd = p.hc2[0];
+            if (NB > 1) hd1 = p.hc2[htile(1, 1) * 32];
+        }
+        if (warp == NW - 1 && NB > 2) hd = p.hc2[htile(2, 2) * 32];     // look-ahead worker (u == 0)
         p.cp.c00 = nug + psill;
         p.cp.psill_eff = rng != 0.0 ? psill : 0.0;            // range == 0: pure nugget model (interp.R:223-227)
         p.cp.nir = rng != 0.0 ? -1.0 / rng : 0.0;
@@ -574,8 +624,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
                 const double2 v = cov_tile(tl2[(T0 + c) * 32], 8 * (NB - 1) + p.r8, 8 * c + 2 * p.q4, n, p.cp, tab32, plain);
                 tl2[(T0 + c) * 32] = make_double2(-v.x, -v.y);
             }
-            if (warp == 0) p.Nd2[0] = neg_cov_diag(p, 0, hd);
-            if (warp == 1) p.Nd2[32] = neg_cov_diag(p, 1, hd);
+            if (warp == NW) {
+                p.Nd2[0] = neg_cov_diag(p, 0, hd);
+                p.Nd2[32] = neg_cov_diag(p, 1, hd1);
+            }
         }
         const long long tp4 = KCLK();
         __syncthreads();
@@ -591,23 +643,30 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
             D.x = -D.x; D.y = -D.y;                           // V_00
             bool singular = false;
             for (int K = 0; K < NB; ++K) {
-                double2 w;
+                double2 zt;
                 const long long tc0 = KCLK();
-                const bool ok = chol8_inverse(D, w, lane);
-                w.x = -w.x; w.y = -w.y;
+#if TWXI_KED_FAKE == 1
+                const bool ok = true; zt = D;
+#else
+                const bool ok = chol8_inverse_t(D, zt, lane);
+#endif
                 t_x += KCLK() - tc0;
-                Wt2[(K & 1) * 32 + lane] = w;
+                {   // publish -inv(L_KK) row-major: lane (c, q) holds Z[c][2q..2q+1] = W[2q..2q+1][c]
+                    double* Wd = reinterpret_cast<double*>(Wt2) + (K & 1) * 64;
+                    Wd[16 * p.q4 + p.r8] = -zt.x;
+                    Wd[16 * p.q4 + 8 + p.r8] = -zt.y;
+                }
                 if (!ok && lane == 0) flag[0] = 1;
                 const long long tb0 = KCLK();
                 named_bar_sync(1, NT);                        // -inv(L_KK) published; the workers' stage K-1 is complete
                 const long long tb1 = KCLK();
                 t_bar += tb1 - tb0;
                 if (flag[0]) { singular = true; break; }
+                const double2 w = Wt2[(K & 1) * 32 + lane];
                 const int rb = ltile(K + 1, 0);
                 double2 l = make_double2(0.0, 0.0);
                 dmma2(l, tl2[(rb + K) * 32], w);              // L(K+1,K) = N(K+1,K) (-W)'
-                double2 nd = Nd2[((K + 1) & 1) * 32 + lane];
-                if (K >= 1) { const double2 t = tl2[(rb + K - 1) * 32]; dmma2(nd, t, t); }
+                double2 nd = Nd2[((K + 1) & 1) * 32 + lane];  // -V + sum_{J<K} L(K+1,J) L(K+1,J)'
                 dmma2(nd, l, l);
                 D.x = -nd.x; D.y = -nd.y;                     // D_{K+1}; for K+1 == NB this is -S
 #ifdef TWXI_KED_PROFILE
@@ -639,16 +698,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
                 if (flag[0]) break;
                 if (c <= NB) {
                     const double2 negW = Wt2[(K & 1) * 32 + lane];
-                    const int rb = ltile(K + 1, 0);
                     double2 lk1 = make_double2(0.0, 0.0);
-                    dmma2(lk1, tl2[(rb + K) * 32], negW);     // L(K+1,K), recomputed by every worker
-                    double2 bK = make_double2(0.0, 0.0);
-                    if (K >= 1) bK = tl2[(rb + K - 1) * 32];  // L(K+1,K-1)
-                    phase_a<NW>(p, K, w, negW, lk1, bK);
-                    const long long ta1 = KCLK();
-                    t_x += ta1 - tb1;
-                    phase_b<NW>(p, c, K, u, vd);
-                    t_y += KCLK() - ta1;
+                    dmma2(lk1, tl2[(ltile(K + 1, 0) + K) * 32], negW);     // L(K+1,K), recomputed by every worker
+                    stage_rows<NW>(p, K, u, negW, lk1, vd);
+                    t_x += KCLK() - tb1;
                 }
             }
             if (warp == 0) { KPROF(9, KCLK() - tp5); KPROF(10, t_bar); KPROF(11, t_x); KPROF(12, t_y); }
@@ -657,15 +710,6 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
     if (warp == NW && pending) ked_finish(a.mean, a.var, a.status, pend_S, pend_q, pend_m, pend_yref, pend_c00, lane);
 }
 
-// Launch configurations: NW worker warps + the diagonal warp.  TWXI_KED_CFG="a,b": NB < a -> 3 workers, NB < b -> 5, else 7.
-static int ked_nw_for(int nbv) {
-    static int t5 = -1, t7 = -1;
-    if (t5 < 0) {
-        t5 = 13; t7 = 13;
-        if (const char* e = getenv("TWXI_KED_CFG")) sscanf(e, "%d,%d", &t5, &t7);
-    }
-    return nbv < t5 ? 3 : (nbv < t7 ? 5 : 7);
-}
 static size_t ked_smem_for(int nbv) { return (size_t)(KED_HDR + (nbv * (nbv + 1) / 2) * 64) * sizeof(double); }
 
 struct KedWork {                 // device scratch of the kriging stage, owned per thread
@@ -675,8 +719,26 @@ struct KedWork {                 // device scratch of the kriging stage, owned p
     size_t list_cap = 0;
     int32_t* bins = nullptr;     // bcount | bstart | fill, each KED_MAXNB+1
     int sms = 0;
-    int occ[4][KED_MAXNB + 1];   // resident CTAs per SM for (NW = 3 / 5 / 7 / 3 with 64 registers, size class)
+    int occ[8][KED_MAXNB + 1];   // resident CTAs per SM for (variant, size class)
+    int var_for[KED_MAXNB + 1];  // variant chosen for each size class
 };
+
+// Launch variants: NW worker warps + the diagonal warp, minimum resident CTAs (register cap), largest n served.
+// Small systems have little panel work per pivot tile, so they run with fewer workers and more CTAs in flight: the
+// kernel is bound by the serial pivot chain of each problem times the problems resident per SM.
+struct KedVariant {
+    void (*fn)(KedArgs);
+    int nw, nmax;
+};
+static const KedVariant KED_VARIANTS[] = {
+    {ked_kernel<1, 16, 64>, 1, 64},
+    {ked_kernel<2, 10, 96>, 2, 96},
+    {ked_kernel<3, 8, 128>, 3, 128},
+    {ked_kernel<3, 6, 128>, 3, 128},
+    {ked_kernel<5, 4, 192>, 5, 192},
+    {ked_kernel<7, 3, 255>, 7, 255},
+};
+constexpr int KED_NVARIANTS = sizeof(KED_VARIANTS) / sizeof(KED_VARIANTS[0]);
 static thread_local KedWork g_ked;
 constexpr int KED_NBMAX = 21;
 
@@ -697,20 +759,24 @@ int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
         TWXI_CUDA(cudaGetDeviceProperties(&p, c.device));
         TWXI_CUDA(cudaMalloc((void**)&w.bins, 3 * (KED_MAXNB + 1) * sizeof(int32_t)));
         const int smem_max = (int)ked_smem_for(KED_NBMAX);
-        TWXI_CUDA(cudaFuncSetAttribute(ked_kernel<3, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-        TWXI_CUDA(cudaFuncSetAttribute(ked_kernel<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-        TWXI_CUDA(cudaFuncSetAttribute(ked_kernel<5, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-        TWXI_CUDA(cudaFuncSetAttribute(ked_kernel<7, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        for (int v = 0; v < KED_NVARIANTS; ++v)
+            TWXI_CUDA(cudaFuncSetAttribute(KED_VARIANTS[v].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        // default choice per size class (measured on B200, profiles/ked_variants_r01.txt); TWXI_KED_VAR overrides it with
+        // one digit (variant index) per size class NB = 1, 2, ...
+        static const char* dflt = "222222223333444455555";
+        const char* sel = getenv("TWXI_KED_VAR");
+        if (!sel || (int)strlen(sel) < KED_NBMAX) sel = dflt;
         for (int nb = 1; nb <= KED_NBMAX; ++nb) {
-            int o3 = 0, o5 = 0, o7 = 0, o38 = 0;
-            TWXI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o38, ked_kernel<3, 8>, 128, ked_smem_for(nb)));
-            w.occ[3][nb] = std::max(1, o38);
-            TWXI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, ked_kernel<3, 6>, 128, ked_smem_for(nb)));
-            TWXI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o5, ked_kernel<5, 4>, 192, ked_smem_for(nb)));
-            TWXI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o7, ked_kernel<7, 3>, 256, ked_smem_for(nb)));
-            w.occ[0][nb] = std::max(1, o3);
-            w.occ[1][nb] = std::max(1, o5);
-            w.occ[2][nb] = std::max(1, o7);
+            for (int v = 0; v < KED_NVARIANTS; ++v) {
+                int o = 0;
+                TWXI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, KED_VARIANTS[v].fn, (KED_VARIANTS[v].nw + 1) * 32,
+                                                                        ked_smem_for(nb)));
+                w.occ[v][nb] = std::max(1, o);
+            }
+            int v = sel[nb - 1] - '0';
+            if (v < 0 || v >= KED_NVARIANTS) v = KED_NVARIANTS - 1;
+            while (KED_VARIANTS[v].nmax < 8 * nb) ++v;        // the variant must cover n = 8 NB
+            w.var_for[nb] = v;
         }
         w.sms = p.multiProcessorCount;
     }
@@ -760,14 +826,9 @@ int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
         for (int nbv = nbmax; nbv >= 1; --nbv) {
             a.nbv = nbv;
             const size_t smem = ked_smem_for(nbv);
-            const int nw = ked_nw_for(nbv);
-            const bool small = nw == 3 && w.occ[3][nbv] > w.occ[0][nbv];      // shared memory leaves room for > 6 CTAs
-            const int occ = small ? w.occ[3][nbv] : w.occ[(nw - 3) / 2][nbv];
-            const int grid = std::min(w.sms * occ, std::max(1, nt));
-            if (small) ked_kernel<3, 8><<<grid, 128, smem, c.stream>>>(a);
-            else if (nw == 7) ked_kernel<7, 3><<<grid, 256, smem, c.stream>>>(a);
-            else if (nw == 5) ked_kernel<5, 4><<<grid, 192, smem, c.stream>>>(a);
-            else ked_kernel<3, 6><<<grid, 128, smem, c.stream>>>(a);
+            const int v = w.var_for[nbv];
+            const int grid = std::min(w.sms * w.occ[v][nbv], std::max(1, nt));
+            KED_VARIANTS[v].fn<<<grid, (KED_VARIANTS[v].nw + 1) * 32, smem, c.stream>>>(a);
             TWXI_LAUNCH_CHECK();
         }
     }

@@ -219,3 +219,22 @@ def test_fixer_window_without_valid_day():
     bad = ref["status"] != 0
     assert np.all(out["tmin"][:, bad] == -32767) and np.all(out["ninvalid"][bad] == -2147483647)
     assert np.array_equal(out["ninvalid"], ref["ninvalid"])
+
+
+def test_grid_knn_candidate_pruning_is_exact(env, monkeypatch):
+    """Work chunks search neighbours over per-block candidate lists (csrc/knn.cu, knn_candidates_kernel).  The lists
+    are supersets of every cell's k+1 nearest stations, so the chunk output must be byte-identical to the full-table
+    scan (TWXI_KNN_FULL=1) — on a ragged chunk (sides not multiples of the 25-cell block) with masked cells."""
+    from topowx_b200.context import TwxiContext, interp_chunk
+    synth, db = env["synth"], env["db"]
+    ctx = [TwxiContext(d, np.isnan(d.stns[db.BAD])) for d in env["da"]]
+    wrk = synth.make_wrk_chk(env["f"], synth.TILE_ROW0 + 20, synth.TILE_COL0 + 40, 60, 83)
+    wrk[2, 5:9, :] = 0                                              # masked rows
+    wrk[2, :, 30] = 0
+    pruned = interp_chunk(ctx[0], ctx[1], wrk)
+    monkeypatch.setenv("TWXI_KNN_FULL", "1")
+    full = interp_chunk(ctx[0], ctx[1], wrk)
+    monkeypatch.delenv("TWXI_KNN_FULL")
+    assert (pruned["status"] == 255).sum() == 4 * 83 + 60 - 4
+    for k in ("tmin", "tmax", "tmin_norm", "tmax_norm", "tmin_se", "tmax_se", "ninvalid", "status"):
+        assert np.array_equal(pruned[k], full[k]), k

@@ -14,6 +14,44 @@ void set_error(const std::string&) {}
 thread_local long long g_launches = 0;
 }
 
+// the round-1 shuffle-based pivot-tile factorisation (KED v3), kept here as the baseline of the comparison
+// Factor the 8x8 SPD tile held in C-fragment layout by one warp and return W = inv(L), L = its Cholesky factor
+// (lower triangular, same layout).  lane = 4*r + q holds columns 2q, 2q+1 of row r.  Computed as an LDL'
+// elimination, W = D^-1/2 inv(L^) (L^ unit lower): the serial dependency per pivot is one shuffle, one
+// reciprocal and one FMA; the column broadcasts, the multiplier products and the elimination of the identity
+// are off that chain, and the 8 square roots are taken once at the end.  Returns false on a non-positive pivot.
+__device__ __forceinline__ bool chol8_inverse(double2 a, double2& w, int lane) {
+    const int r = lane >> 2, q = lane & 3;
+    w.x = (2 * q == r) ? 1.0 : 0.0;
+    w.y = (2 * q + 1 == r) ? 1.0 : 0.0;
+    bool ok = true;
+    double prow = 1.0;                                        // 1 / d_r of my row
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int kq = k >> 1;
+        const double mine = (k & 1) ? a.y : a.x;             // my element of column k (valid if q == kq)
+        const double dk = __shfl_sync(0xffffffffu, mine, 4 * k + kq);
+        const double ci = __shfl_sync(0xffffffffu, mine, 4 * r + kq);              // a[r][k]
+        const double cj0 = __shfl_sync(0xffffffffu, mine, 4 * (2 * q) + kq);       // a[2q][k]
+        const double cj1 = __shfl_sync(0xffffffffu, mine, 4 * (2 * q + 1) + kq);   // a[2q+1][k]
+        ok = ok && (dk > 0.0);                                // NaN fails; inf is caught by the final isfinite
+        const double p = fast_rcp(dk);
+        if (r == k) prow = p;
+        const double t0 = ci * cj0, t1 = ci * cj1;
+        if (2 * q > k) a.x = fma(-t0, p, a.x);
+        if (2 * q + 1 > k) a.y = fma(-t1, p, a.y);
+        // forward elimination of the identity with the unit-lower multipliers m = a[r][k] / d_k
+        const double m = ci * p;
+        const double wkx = __shfl_sync(0xffffffffu, w.x, 4 * k + q);
+        const double wky = __shfl_sync(0xffffffffu, w.y, 4 * k + q);
+        if (r > k) { w.x = fma(-m, wkx, w.x); w.y = fma(-m, wky, w.y); }
+    }
+    const double sp = sqrt(prow);
+    w.x *= sp; w.y *= sp;
+    return ok;
+}
+
+
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
 
 __global__ void k_lat(long long* out, int iters, double a, double b) {
@@ -48,7 +86,6 @@ __global__ void k_chol(long long* out, const double* tiles, int reps, double* wo
         bool ok = true;
         for (int i = 0; i < reps; ++i) {
             if (VARIANT == 0) ok &= chol8_inverse(a, w, lane);
-            else if (VARIANT == 1) ok &= chol8_inverse_ff(a, w, lane);
             else {
                 double2 z;
                 ok &= chol8_inverse_t(a, z, lane);
@@ -112,14 +149,13 @@ int main() {
     for (int c = 0; c < 8; ++c) for (int i = 0; i < 8; ++i) { double s = (i == c) ? 1.0 : 0.0; for (int k = 0; k < i; ++k) s -= L[i][k] * W[k][c]; W[i][c] = s / L[i][i]; }
 
     const int reps = 200;
-    for (int variant = 0; variant < 3; ++variant) {
+    for (int variant = 0; variant < 2; ++variant) {
         for (int nwarps : {1, 4}) {
             for (int ctas_per_sm : {1, 2}) {
                 if (nwarps * ctas_per_sm > 32) continue;
                 const int grid = 148 * ctas_per_sm;
                 if (variant == 0) k_chol<0><<<grid, 32 * nwarps>>>(d_out, d_tiles, reps, d_w);
-                else if (variant == 1) k_chol<1><<<grid, 32 * nwarps>>>(d_out, d_tiles, reps, d_w);
-                else k_chol<2><<<grid, 32 * nwarps>>>(d_out, d_tiles, reps, d_w);
+                else k_chol<1><<<grid, 32 * nwarps>>>(d_out, d_tiles, reps, d_w);
                 CK(cudaDeviceSynchronize());
                 std::vector<long long> o(grid * 2);
                 CK(cudaMemcpy(o.data(), d_out, grid * 16, cudaMemcpyDeviceToHost));

@@ -109,6 +109,7 @@ static int load_points(Ctx& c, const twxi_points* p, int k1, bool need_daily) {
     if (p->lst) TWXI_CUDA(cudaMemcpyAsync(b.lst, p->lst, n * 96, cudaMemcpyDefault, c.stream));
     b.n_rm = p->rm_idx ? p->n_rm : 0;
     b.rm_zero = p->rm_zero_dist;
+    b.gy = b.gx = 0;
     if (b.n_rm > 0)
         TWXI_CUDA(cudaMemcpyAsync(b.rm_idx, p->rm_idx, n * b.n_rm * 4, cudaMemcpyDefault, c.stream));
     TWXI_CUDA(cudaMemsetAsync(b.status, 0, n * 4, c.stream));
@@ -118,7 +119,7 @@ static int load_points(Ctx& c, const twxi_points* p, int k1, bool need_daily) {
 static int run_knn(Ctx& c) {
     Batch& b = c.b;
     return launch_knn(c, b.npts, b.lat, b.lon, b.n_rm ? b.rm_idx : nullptr, b.n_rm, b.rm_zero, b.k1, b.idx, b.dist,
-                      nullptr, b.status);
+                      nullptr, b.status, b.gy, b.gx);
 }
 
 struct StageTimer {
@@ -648,6 +649,8 @@ int twxi_interp_chunk(twxi_ctx* cmin, twxi_ctx* cmax, const double* wrk_chk, int
         if ((rc = ensure_batch(*cmax, ncell, default_k1(*cmax), daily)) != TWXI_OK) break;
         cmin->b.n_rm = cmax->b.n_rm = 0;
         cmin->b.rm_zero = cmax->b.rm_zero = 0;
+        cmin->b.gy = cmax->b.gy = ny;
+        cmin->b.gx = cmax->b.gx = nx;
         const int nd = daily ? cmin->ob.ndays : 0;
         const bool host = !(mem == TWXI_MEM_DEVICE);
         // device staging of the chunk and of the results when the caller's buffers are on the host

@@ -7,15 +7,16 @@
 //     daily_t = z . (obs_t - norm) + pt_norm = z . obs_t + (pt_norm - z . norm).
 // The 6x6 normal equations are accumulated with the predictors centred on the point and scaled (exactly the
 // same predictor because the intercept is in X; the reference inverts the uncentred matrix with LAPACK, which
-// loses ~5 digits it never needed), factored by Cholesky in registers, and the hat row is kept in shared
-// memory while the warp streams the month's days: lanes = days, neighbours gathered from the station-major,
+// loses ~5 digits it never needed) as DMMA outer products, solved with the tensor-pipe pivot-tile factorisation of
+// the kriging kernel (chol8_inverse_t), and the hat row is kept in shared memory while the warp streams the month's
+// days: lanes = days, neighbours gathered from the station-major,
 // month-major observation table (coalesced 128 B per neighbour, L2 resident).
 // One warp per (point, month); no intermediate hat rows go to HBM unless the caller asks for them.
 #include "twxi_internal.cuh"
 
 namespace twxi {
 
-constexpr int GWR_THREADS = 128;
+constexpr int GWR_THREADS = 256;
 constexpr int GWR_WARPS = GWR_THREADS / 32;
 constexpr int GWR_MAXK = 256;
 
@@ -38,15 +39,17 @@ struct GwrArgs {
     int32_t* status;
 };
 
-__global__ void __launch_bounds__(GWR_THREADS) gwr_kernel(GwrArgs a) {
-    __shared__ double s_z[GWR_WARPS][GWR_MAXK];
-    __shared__ int s_idx[GWR_WARPS][GWR_MAXK];
+__global__ void __launch_bounds__(GWR_THREADS, 4) gwr_kernel(GwrArgs a) {
+    __shared__ __align__(16) double s_z[GWR_WARPS][GWR_MAXK];
+    __shared__ __align__(16) int s_off[GWR_WARPS][GWR_MAXK];                // station * ndays: row offset into obsT
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nm = a.single_mth >= 0 ? 1 : 12;
     const long long item = (long long)blockIdx.x * GWR_WARPS + warp;
     if (item >= (long long)a.npts * nm) return;
-    const int q = (int)(item / nm);
-    const int m = a.single_mth >= 0 ? a.single_mth : (int)(item % nm);
+    // month-major items: the warps of a CTA work on the same month of consecutive (= adjacent) points, whose neighbour
+    // sets nearly coincide, so the station predictors and observation lines they gather are shared through L1
+    const int q = (int)(item % a.npts);
+    const int m = a.single_mth >= 0 ? a.single_mth : (int)(item / a.npts);
     if (a.status[q] != TWXI_ST_OK) return;
     const int k = a.nn[(size_t)q * 24 + 12 + m];
     if (k < 1) return;
@@ -59,92 +62,81 @@ __global__ void __launch_bounds__(GWR_THREADS) gwr_kernel(GwrArgs a) {
     const double* lstm = a.st.lst + (size_t)m * N;
     const double* normm = a.st.norm + (size_t)m * N;
 
-    // ---- X'WX (lower triangle, 21 sums) ------------------------------------------------------------------
-    double A[21];
-#pragma unroll
-    for (int i = 0; i < 21; ++i) A[i] = 0.0;
-    for (int j = lane; j < k; j += 32) {
-        const int s = idx[j];
-        s_idx[warp][j] = s;
-        const double r = dist[j] / dbw;
-        const double u = __dsub_rn(1.0, __dmul_rn(r, r));
-        const double w = __dmul_rn(u, u);                     // bisquare, station_select.py:169
-        double x[6] = {1.0, a.st.lon[s] - lon0, a.st.lat[s] - lat0, (a.st.elev[s] - elev0) * 1e-3,
-                       a.st.tdi[s] - tdi0, (lstm[s] - lst0) * 0.1};
-        int t = 0;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            const double wx = w * x[i];
-#pragma unroll
-            for (int jj = 0; jj <= i; ++jj) A[t++] += wx * x[jj];
+    // ---- X'WX on the tensor pipe --------------------------------------------------------------------------
+    // Lane (i, kk) = (lane / 4, lane % 4) supplies predictor i of station 4t + kk scaled by sqrt(w) = 1 - (d/dbw)^2
+    // (bisquare w = (1 - (d/dbw)^2)^2, station_select.py:169); the same register is the A and the B operand of one
+    // DMMA, which adds the four outer products sqrt(w) x (sqrt(w) x)' of those stations to the 8x8 accumulator.
+    const int pi = lane >> 2, kk = lane & 3;
+    const double* src = a.st.lon;
+    double ref = 0.0, scl = 0.0, cst = 0.0;                   // predictor = (src[s] - ref) * scl + cst
+    if (pi == 0) cst = 1.0;
+    else if (pi == 1) { ref = lon0; scl = 1.0; }
+    else if (pi == 2) { src = a.st.lat; ref = lat0; scl = 1.0; }
+    else if (pi == 3) { src = a.st.elev; ref = elev0; scl = 1e-3; }
+    else if (pi == 4) { src = a.st.tdi; ref = tdi0; scl = 1.0; }
+    else if (pi == 5) { src = lstm; ref = lst0; scl = 0.1; }
+    // stage the neighbour indices and sqrt(w) once per station (coalesced), padded to a multiple of 16 with weight 0
+    const int kpad = (k + 15) & ~15;
+    for (int j = lane; j < kpad; j += 32) {
+        int sj = 0;
+        double uj = 0.0;
+        if (j < k) {
+            sj = idx[j];
+            const double r = dist[j] / dbw;
+            uj = __dsub_rn(1.0, __dmul_rn(r, r));
         }
+        s_off[warp][j] = sj;
+        s_z[warp][j] = uj;
     }
+    __syncwarp();
+    double2 c0 = make_double2(0.0, 0.0), c1 = c0, c2 = c0, c3 = c0;
+    for (int j0 = 0; j0 < kpad; j0 += 16) {
+        double v[4];
 #pragma unroll
-    for (int i = 0; i < 21; ++i) A[i] = warp_sum(A[i]);
+        for (int e = 0; e < 4; ++e) {
+            const int j = j0 + 4 * e + kk;
+            v[e] = s_z[warp][j] * fma(src[s_off[warp][j]] - ref, scl, cst);
+        }
+        dmma(c0, v[0], v[0]); dmma(c1, v[1], v[1]); dmma(c2, v[2], v[2]); dmma(c3, v[3], v[3]);
+    }
+    double2 A = make_double2((c0.x + c1.x) + (c2.x + c3.x), (c0.y + c1.y) + (c2.y + c3.y));
+    if (lane == 4 * 6 + 3) A.x = 1.0;                         // identity padding of rows / columns 6, 7
+    if (lane == 4 * 7 + 3) A.y = 1.0;
 
-    // ---- Cholesky of the 6x6, solve A u = e1 (every lane redundantly) -----------------------------------
-    bool ok = true;
-    double L[6][6];
-    {
-        int t = 0;
-#pragma unroll
-        for (int i = 0; i < 6; ++i)
-#pragma unroll
-            for (int jj = 0; jj <= i; ++jj) L[i][jj] = A[t++];
-    }
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-        double d = L[j][j];
-#pragma unroll
-        for (int kk = 0; kk < j; ++kk) d -= L[j][kk] * L[j][kk];
-        ok = ok && (d > 0.0) && (d < 1e300);
-        const double l = sqrt(d);
-        L[j][j] = l;
-#pragma unroll
-        for (int i = j + 1; i < 6; ++i) {
-            double sacc = L[i][j];
-#pragma unroll
-            for (int kk = 0; kk < j; ++kk) sacc -= L[i][kk] * L[j][kk];
-            L[i][j] = sacc / l;
-        }
-    }
+    // ---- u = (X'WX)^-1 e_0 from the transposed inverse Cholesky factor Z: (X'WX)^-1 = Z Z' ------------------
+    double2 z;
+    bool ok = chol8_inverse_t(A, z, lane);
+    const double r0x = __shfl_sync(0xffffffffu, z.x, kk), r0y = __shfl_sync(0xffffffffu, z.y, kk);   // row 0 of Z
+    double part = fma(z.x, r0x, z.y * r0y);
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);            // u_i in the four lanes of row i
     double u[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
-        double sacc = (i == 0) ? 1.0 : 0.0;
-#pragma unroll
-        for (int kk = 0; kk < i; ++kk) sacc -= L[i][kk] * u[kk];
-        u[i] = sacc / L[i][i];
+        u[i] = __shfl_sync(0xffffffffu, part, 4 * i);
+        ok = ok && isfinite(u[i]);
     }
-#pragma unroll
-    for (int i = 5; i >= 0; --i) {
-        double sacc = u[i];
-#pragma unroll
-        for (int kk = i + 1; kk < 6; ++kk) sacc -= L[kk][i] * u[kk];
-        u[i] = sacc / L[i][i];
-    }
-#pragma unroll
-    for (int i = 0; i < 6; ++i) ok = ok && isfinite(u[i]);
     if (!ok) {
         if (lane == 0) atomicCAS(a.status + q, TWXI_ST_OK, TWXI_ST_SINGULAR);
         return;
     }
 
     // ---- hat row z_j = w_j * (x_j . u) and offset pt_norm - z . norm -------------------------------------
+    const size_t nd = (size_t)a.ob.ndays;
     double zn = 0.0;
     for (int j = lane; j < k; j += 32) {
-        const int s = s_idx[warp][j];
-        const double r = dist[j] / dbw;
-        const double uu = __dsub_rn(1.0, __dmul_rn(r, r));
+        const int s = s_off[warp][j];
+        const double uu = s_z[warp][j];
         const double w = __dmul_rn(uu, uu);
         const double xu = u[0] + u[1] * (a.st.lon[s] - lon0) + u[2] * (a.st.lat[s] - lat0)
                           + u[3] * ((a.st.elev[s] - elev0) * 1e-3) + u[4] * (a.st.tdi[s] - tdi0)
                           + u[5] * ((lstm[s] - lst0) * 0.1);
-        const double z = w * xu;
-        s_z[warp][j] = z;
-        zn += z * normm[s];
+        const double zj = w * xu;
+        s_z[warp][j] = zj;
+        s_off[warp][j] = s * (int)nd;
+        zn += zj * normm[s];
         if (a.hat_z) {
-            a.hat_z[(size_t)q * a.kmax + j] = z;
+            a.hat_z[(size_t)q * a.kmax + j] = zj;
             a.hat_idx[(size_t)q * a.kmax + j] = s;
         }
     }
@@ -153,26 +145,30 @@ __global__ void __launch_bounds__(GWR_THREADS) gwr_kernel(GwrArgs a) {
     __syncwarp();
     if (!a.daily && !a.out_month) return;
 
+    // ---- daily values: lanes = days of the month, neighbours gathered from the station-major obs table ------------
     const double ptn = a.pt_norm_single ? a.pt_norm[q] : a.pt_norm[(size_t)q * 12 + m];
     const double off = ptn - zn;
     const int p0 = a.ob.moff[m], D = a.ob.moff[m + 1] - p0;
-    const size_t nd = (size_t)a.ob.ndays;
     for (int d0 = 0; d0 < D; d0 += 32) {
         const int d = d0 + lane;
         const bool valid = d < D;
-        const size_t p = (size_t)p0 + (valid ? d : 0);
-        double acc0 = 0.0, acc1 = 0.0;
+        const float* col = a.ob.obsT + p0 + (valid ? d : 0);
+        double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
         int j = 0;
-        for (; j + 1 < k; j += 2) {
-            const float o0 = a.ob.obsT[(size_t)s_idx[warp][j] * nd + p];
-            const float o1 = a.ob.obsT[(size_t)s_idx[warp][j + 1] * nd + p];
-            acc0 = fma(s_z[warp][j], (double)o0, acc0);
-            acc1 = fma(s_z[warp][j + 1], (double)o1, acc1);
+        for (; j + 3 < k; j += 4) {                           // four gathers in flight per pass
+            const int4 o4 = *reinterpret_cast<const int4*>(&s_off[warp][j]);
+            const float f0 = col[o4.x], f1 = col[o4.y], f2 = col[o4.z], f3 = col[o4.w];
+            const double2 za = *reinterpret_cast<const double2*>(&s_z[warp][j]);
+            const double2 zb = *reinterpret_cast<const double2*>(&s_z[warp][j + 2]);
+            acc0 = fma(za.x, (double)f0, acc0);
+            acc1 = fma(za.y, (double)f1, acc1);
+            acc2 = fma(zb.x, (double)f2, acc2);
+            acc3 = fma(zb.y, (double)f3, acc3);
         }
-        if (j < k) acc0 = fma(s_z[warp][j], (double)a.ob.obsT[(size_t)s_idx[warp][j] * nd + p], acc0);
-        const double v = (acc0 + acc1) + off;
+        for (; j < k; ++j) acc0 = fma(s_z[warp][j], (double)col[s_off[warp][j]], acc0);
+        const double v = ((acc0 + acc1) + (acc2 + acc3)) + off;
         if (valid) {
-            if (a.daily) a.daily[(size_t)q * nd + a.ob.day_of_pos[p]] = v;
+            if (a.daily) a.daily[(size_t)q * nd + a.ob.day_of_pos[p0 + d]] = v;
             if (a.out_month) a.out_month[(size_t)q * D + d] = v;
         }
     }

@@ -76,142 +76,10 @@ struct KedArgs {
     int32_t* status;
 };
 
-__device__ __forceinline__ void dmma(double2& c, double a, double b) {
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-        : "+d"(c.x), "+d"(c.y) : "d"(a), "d"(b));
-}
-// c += X * Y' for two 8x8 tiles in C-fragment layout (even columns, then odd columns)
-__device__ __forceinline__ void dmma2(double2& c, const double2& x, const double2& y) {
-    dmma(c, x.x, y.x);
-    dmma(c, x.y, y.y);
-}
 // shared-memory L tiles: rows 1..NBv, row I holds tiles J = 0..I-1 (diagonal tiles are never stored)
 __device__ __forceinline__ int ltile(int I, int J) { return I * (I - 1) / 2 + J; }
 // compact distance tiles: rows 0..NB-1, row I holds tiles J = 0..I
 __device__ __forceinline__ int htile(int I, int J) { return I * (I + 1) / 2 + J; }
-
-// 1/d for a normal positive double without the slow-path branches of the IEEE division: MUFU seed (~2^-20) and one
-// third-order Newton step (error ~ e^3, below 1 ulp).  Non-positive / non-finite pivots are rejected by the caller.
-__device__ __forceinline__ double fast_rcp(double d) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-    const double e = fma(-d, r, 1.0);
-    const double e2 = fma(e, e, e);
-    return fma(r, e2, r);
-}
-
-// Factor the 8x8 SPD tile held in C-fragment layout by one warp and return W = inv(L), L = its Cholesky factor
-// (lower triangular, same layout).  lane = 4*r + q holds columns 2q, 2q+1 of row r.  Computed as an LDL'
-// elimination, W = D^-1/2 inv(L^) (L^ unit lower): the serial dependency per pivot is one shuffle, one
-// reciprocal and one FMA; the column broadcasts, the multiplier products and the elimination of the identity
-// are off that chain, and the 8 square roots are taken once at the end.  Returns false on a non-positive pivot.
-__device__ __forceinline__ bool chol8_inverse(double2 a, double2& w, int lane) {
-    const int r = lane >> 2, q = lane & 3;
-    w.x = (2 * q == r) ? 1.0 : 0.0;
-    w.y = (2 * q + 1 == r) ? 1.0 : 0.0;
-    bool ok = true;
-    double prow = 1.0;                                        // 1 / d_r of my row
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int kq = k >> 1;
-        const double mine = (k & 1) ? a.y : a.x;             // my element of column k (valid if q == kq)
-        const double dk = __shfl_sync(0xffffffffu, mine, 4 * k + kq);
-        const double ci = __shfl_sync(0xffffffffu, mine, 4 * r + kq);              // a[r][k]
-        const double cj0 = __shfl_sync(0xffffffffu, mine, 4 * (2 * q) + kq);       // a[2q][k]
-        const double cj1 = __shfl_sync(0xffffffffu, mine, 4 * (2 * q + 1) + kq);   // a[2q+1][k]
-        ok = ok && (dk > 0.0);                                // NaN fails; inf is caught by the final isfinite
-        const double p = fast_rcp(dk);
-        if (r == k) prow = p;
-        const double t0 = ci * cj0, t1 = ci * cj1;
-        if (2 * q > k) a.x = fma(-t0, p, a.x);
-        if (2 * q + 1 > k) a.y = fma(-t1, p, a.y);
-        // forward elimination of the identity with the unit-lower multipliers m = a[r][k] / d_k
-        const double m = ci * p;
-        const double wkx = __shfl_sync(0xffffffffu, w.x, 4 * k + q);
-        const double wky = __shfl_sync(0xffffffffu, w.y, 4 * k + q);
-        if (r > k) { w.x = fma(-m, wkx, w.x); w.y = fma(-m, wky, w.y); }
-    }
-    const double sp = sqrt(prow);
-    w.x *= sp; w.y *= sp;
-    return ok;
-}
-
-// 1/sqrt(d) for a normal positive double: MUFU seed and one third-order step (error ~ e^3), like fast_rcp.
-__device__ __forceinline__ double fast_rsqrt(double d) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-    const double e = fma(-d * y, y, 1.0);
-    const double g = fma(e, 0.375, 0.5) * e;
-    return fma(y, g, y);
-}
-
-// Tensor-pipe form of the pivot-tile factorisation.  With the tile in C-fragment layout, lane (r, q = k/2) owns
-// M[r][k]; feeding that column (zero in the other lanes) as BOTH operands of one DMMA adds the outer product
-// M[:,k] M[:,k]' to every element at once: no column broadcasts and no predicates (finished rows and columns are exactly
-// zero and stay zero).  Fraction-free (Bareiss) scaling keeps the reciprocal off the serial pivot chain:
-//     M <- (d_k M - M[:,k] M[:,k]') / M(k-1)_(k-1,k-1),   d_k := M(k)_kk  (pivot of LDL' = d_k / previous d).
-// The inverse is accumulated TRANSPOSED, Z = inv(L)': Z[c][r] -= Z[c][k] m_rk needs column k of Z and the multipliers
-// m_rk = M[r][k] / d_k, both already sitting in the lanes (r, q = k/2) that feed the DMMA — no shuffles either.
-// Per pivot: one shuffle (d_k), two DMMAs, ~8 scalar FP64 ops; chain = shuffle + DMUL + DMMA.  The update of Z for
-// pivot k-1 is issued after the shuffle of pivot k so that it runs in the shuffle's shadow (in-order issue).
-// Returns Z scaled by the inverse square roots of the pivots (columns), i.e. the transpose of inv(chol(A)).
-template <int NPIV>
-__device__ __forceinline__ bool elim8_mma(double2& a, int lane) {
-    const int q = lane & 3;
-    bool ok = true;
-    double rprev = 1.0;                                       // 1 / d_(k-1)
-#pragma unroll
-    for (int k = 0; k < NPIV; ++k) {
-        const int kq = k >> 1;
-        const double mine = (k & 1) ? a.y : a.x;
-        const double e = (q == kq) ? mine : 0.0;              // M[r][k] in the lanes that own column k
-        const double dk = __shfl_sync(0xffffffffu, mine, 4 * k + kq);
-        const double ax = a.x * rprev, ay = a.y * rprev;      // in the shadow of the shuffle
-        ok = ok && (dk > 0.0);
-        const double es = -e * rprev;
-        double2 c = make_double2(dk * ax, dk * ay);           // M <- (d_k M - M[:,k] M[:,k]') / previous pivot
-        dmma(c, es, e);
-        a = c;
-        rprev = fast_rcp(dk);
-    }
-    a.x *= rprev; a.y *= rprev;                               // Schur complement of the first NPIV pivots
-    return ok;
-}
-
-// Returns Z = transpose of inv(chol(A)) in C-fragment layout (A = the SPD tile `a`).  The seven Z updates depend on
-// each other only through Z, so the scheduler is free to run them behind the pivot chain.
-__device__ __forceinline__ bool chol8_inverse_t(double2 a, double2& z, int lane) {
-    const int r = lane >> 2, q = lane & 3;
-    z.x = (2 * q == r) ? 1.0 : 0.0;
-    z.y = (2 * q + 1 == r) ? 1.0 : 0.0;
-    bool ok = true;
-    double dx = 1.0, dy = 1.0;                                // LDL' pivots of columns 2q, 2q+1 (scale the columns of Z)
-    double rprev = 1.0;                                       // 1 / d_(k-1)
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int kq = k >> 1;
-        const double mine = (k & 1) ? a.y : a.x;
-        const double e = (q == kq) ? mine : 0.0;              // M[r][k] in the lanes that own column k
-        const double dk = __shfl_sync(0xffffffffu, mine, 4 * k + kq);
-        const double ax = a.x * rprev, ay = a.y * rprev;      // in the shadow of the shuffle
-        ok = ok && (dk > 0.0);
-        const double piv = dk * rprev;
-        if (kq == q) { if (k & 1) dy = piv; else dx = piv; }
-        if (k < 7) {
-            const double es = -e * rprev;
-            double2 c = make_double2(dk * ax, dk * ay);       // M <- (d_k M - M[:,k] M[:,k]') / previous pivot
-            dmma(c, es, e);
-            a = c;
-            const double p = fast_rcp(dk);
-            const double mneg = (r == k) ? 0.0 : -e * p;      // Z[c][r] -= Z[c][k] m_rk
-            dmma(z, (k & 1) ? z.y : z.x, mneg);
-            rprev = p;
-        }
-    }
-    z.x *= fast_rsqrt(dx);
-    z.y *= fast_rsqrt(dy);
-    return ok;
-}
 
 // ---- 1. compact distance tiles -------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) hgather_kernel(StnTable st, int q0, int nq, int k1, const int32_t* idx,

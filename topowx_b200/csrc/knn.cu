@@ -11,6 +11,8 @@
 // Bit-exactness: the "a" term uses the reference's operation order with explicit _rn intrinsics (no FMA
 // contraction).  a -> km is monotone (sqrt is correctly rounded, asin monotone up to its 1-ulp error); the
 // selected set is re-checked in km and re-sorted on (km, index) if asin ever breaks monotonicity.
+#include <algorithm>
+#include <cstdlib>
 #include "twxi_internal.cuh"
 
 namespace twxi {
@@ -33,7 +35,14 @@ struct KnnArgs {
     double* out_dist;
     double* out_wgt;
     int32_t* status;
+    // gridded queries (work chunks): per block of KNN_BLK x KNN_BLK cells a list of candidate stations that is
+    // guaranteed to contain the k1 nearest stations of every cell of the block (null = scan the whole table)
+    const int32_t* cand;       // [nblocks][cand_cap]
+    const int32_t* cand_cnt;   // [nblocks]; < 0: no list for this block, scan the whole table
+    int cand_cap, gx, nbx;
 };
+
+constexpr int KNN_BLK = 25;    // cells per side of a candidate block (the 250 x 250 tiles divide evenly)
 
 __device__ __forceinline__ bool pair_less(unsigned long long ka, int ia, unsigned long long kb, int ib) {
     return ka < kb || (ka == kb && ia < ib);
@@ -69,9 +78,15 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(KnnArgs a) {
 
     const int q = blockIdx.x;
     const int tid = threadIdx.x;
-    const int n = a.n;
     const int k1 = a.k1;
     if (a.status[q] != TWXI_ST_OK) return;                     // masked cell / earlier failure
+    int n = a.n;
+    const int32_t* cand = nullptr;
+    if (a.cand) {
+        const int b = (q / a.gx / KNN_BLK) * a.nbx + (q % a.gx) / KNN_BLK;
+        const int cnt = a.cand_cnt[b];
+        if (cnt >= 0) { cand = a.cand + (size_t)b * a.cand_cap; n = cnt; }
+    }
 
     // ---- phase 1: haversine "a" of every station (util_geo.py:27-36) -------------------------------
     const double lat1rad = __dmul_rn(a.qlat[q], TWX_RAD);
@@ -81,14 +96,15 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(KnnArgs a) {
 #pragma unroll
     for (int i = 0; i < TWXI_MAX_RM; ++i) rm[i] = (i < a.n_rm) ? a.rm_idx[(size_t)q * a.n_rm + i] : -1;
 
-    for (int s = tid; s < n; s += KNN_THREADS) {
+    for (int t = tid; t < n; t += KNN_THREADS) {
+        const int s = cand ? cand[t] : t;
         double av = hav_a(lat1rad, lon1rad, coslat1, a.latrad[s], a.lonrad[s], a.coslat[s]);
         unsigned long long key = (unsigned long long)__double_as_longlong(av);
         bool removed = (a.rm_zero && av == 0.0);               // station_select.py:97-99 (d == 0 <=> a == 0)
 #pragma unroll
         for (int i = 0; i < TWXI_MAX_RM; ++i) removed |= (rm[i] == s);   // :101-104
         if (removed || !(av >= 0.0)) key = ~0ull;
-        keys[s] = key;
+        keys[t] = key;
     }
     if (tid == 0) { s_prefix = 0ull; s_remaining = (unsigned)k1; s_cnt = 0u; }
     __syncthreads();
@@ -154,7 +170,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(KnnArgs a) {
         if (k <= T) {
             unsigned p = atomicAdd(&s_cnt, 1u);
             selkey[p] = k;
-            selidx[p] = s;
+            selidx[p] = cand ? cand[s] : s;
         }
     }
     __syncthreads();
@@ -189,6 +205,81 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(KnnArgs a) {
     }
 }
 
+// Candidate stations of one block of grid cells.  With c the block's centre cell, r_c the distance of its k1-th
+// nearest station and delta the largest distance from c to a cell of the block, the triangle inequality puts the
+// k1 nearest stations of every cell within r_c + 2 delta of c.  The list is a superset, so the per-cell search over it
+// (same arithmetic, same (distance, index) order) returns exactly what the full scan returns.
+__global__ void __launch_bounds__(KNN_THREADS) knn_candidates_kernel(KnnArgs a, int gy, int32_t* cand, int32_t* cand_cnt) {
+    extern __shared__ unsigned long long smem_u64[];
+    unsigned long long* keys = smem_u64;                       // [n]
+    unsigned* hist = reinterpret_cast<unsigned*>(keys + a.n);  // [256]
+    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned s_remaining, s_cnt;
+    __shared__ double s_delta[KNN_THREADS / 32];
+    const int tid = threadIdx.x, n = a.n, k1 = a.k1, gx = a.gx;
+    const int by = blockIdx.x / a.nbx, bx = blockIdx.x % a.nbx;
+    const int y0 = by * KNN_BLK, x0 = bx * KNN_BLK;
+    const int y1 = min(y0 + KNN_BLK, gy), x1 = min(x0 + KNN_BLK, gx);
+    const int qc = ((y0 + y1 - 1) / 2) * gx + (x0 + x1 - 1) / 2;
+    const double latc = __dmul_rn(a.qlat[qc], TWX_RAD), lonc = __dmul_rn(a.qlon[qc], TWX_RAD), cosc = cos(latc);
+    for (int s = tid; s < n; s += KNN_THREADS) {
+        const double av = hav_a(latc, lonc, cosc, a.latrad[s], a.lonrad[s], a.coslat[s]);
+        keys[s] = (av >= 0.0) ? (unsigned long long)__double_as_longlong(av) : ~0ull;
+    }
+    // delta: farthest cell of the block from the centre cell
+    double dmax = 0.0;
+    const int w = x1 - x0, cells = (y1 - y0) * w;
+    for (int t = tid; t < cells; t += KNN_THREADS) {
+        const int q = (y0 + t / w) * gx + x0 + t % w;
+        const double la = __dmul_rn(a.qlat[q], TWX_RAD), lo = __dmul_rn(a.qlon[q], TWX_RAD);
+        dmax = fmax(dmax, hav_km(hav_a(latc, lonc, cosc, la, lo, cos(la))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    if ((tid & 31) == 0) s_delta[tid >> 5] = dmax;
+    if (tid == 0) { s_prefix = 0ull; s_remaining = (unsigned)k1; s_cnt = 0u; }
+    __syncthreads();
+    for (int pass = 0; pass < 8; ++pass) {                     // k1-th smallest key of the centre cell
+        const int shift = 56 - 8 * pass;
+        const unsigned long long mask = pass == 0 ? 0ull : (~0ull << (shift + 8));
+        hist[tid] = 0u;
+        __syncthreads();
+        const unsigned long long prefix = s_prefix;
+        for (int s = tid; s < n; s += KNN_THREADS) {
+            const unsigned long long k = keys[s];
+            if ((k & mask) == prefix) atomicAdd(&hist[(unsigned)(k >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned rem = s_remaining, acc = 0;
+            for (int b = 0; b < 256; ++b) {
+                if (acc + hist[b] >= rem) { s_prefix = prefix | ((unsigned long long)b << shift); s_remaining = rem - acc; break; }
+                acc += hist[b];
+            }
+        }
+        __syncthreads();
+    }
+    const unsigned long long T = s_prefix;
+    if (T == ~0ull) {                                          // fewer than k1 stations: every cell reports it itself
+        if (tid == 0) cand_cnt[blockIdx.x] = -1;
+        return;
+    }
+    double delta = 0.0;
+    for (int i = 0; i < KNN_THREADS / 32; ++i) delta = fmax(delta, s_delta[i]);
+    const double rc = hav_km(__longlong_as_double((long long)T));
+    const double R = (rc + 2.0 * delta) * (1.0 + 1e-9) + 1e-6;
+    int32_t* out = cand + (size_t)blockIdx.x * a.cand_cap;
+    for (int s = tid; s < n; s += KNN_THREADS) {
+        const unsigned long long k = keys[s];
+        if (k != ~0ull && hav_km(__longlong_as_double((long long)k)) <= R) {
+            const unsigned p = atomicAdd(&s_cnt, 1u);
+            if (p < (unsigned)a.cand_cap) out[p] = s;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) cand_cnt[blockIdx.x] = s_cnt <= (unsigned)a.cand_cap ? (int)s_cnt : -1;
+}
+
 __global__ void station_trig_kernel(int n, const double* lon, const double* lat, double* lonrad, double* latrad,
                                     double* coslat) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -220,13 +311,47 @@ int launch_build_dist_table(cudaStream_t s, int n, const double* lon, const doub
     return TWXI_OK;
 }
 
+struct KnnWork {                 // candidate lists of the gridded search, owned per thread
+    int32_t* cand = nullptr;
+    int32_t* cnt = nullptr;
+    size_t cand_elems = 0, cnt_elems = 0;
+};
+static thread_local KnnWork g_knn;
+constexpr int KNN_CAND_CAP = 1024;
+
 int launch_knn(Ctx& c, int npts, const double* lat, const double* lon, const int32_t* rm_idx, int n_rm,
-               int rm_zero, int k1, int32_t* idx, double* dist, double* wgt, int32_t* status) {
+               int rm_zero, int k1, int32_t* idx, double* dist, double* wgt, int32_t* status, int gy, int gx) {
     if (npts <= 0) return TWXI_OK;
     KnnArgs a;
     a.n = c.n; a.latrad = c.st.latrad; a.lonrad = c.st.lonrad; a.coslat = c.st.coslat;
     a.qlat = lat; a.qlon = lon; a.rm_idx = rm_idx; a.n_rm = rm_idx ? n_rm : 0; a.rm_zero = rm_zero; a.k1 = k1;
     a.out_idx = idx; a.out_dist = dist; a.out_wgt = wgt; a.status = status;
+    a.cand = nullptr; a.cand_cnt = nullptr; a.cand_cap = 0; a.gx = 0; a.nbx = 0;
+    // gridded queries without leave-outs: prune the station table once per block of cells
+    if (gy > 0 && gx > 0 && (long long)gy * gx == npts && a.n_rm == 0 && !rm_zero && c.n > 2 * k1 && !getenv("TWXI_KNN_FULL")) {
+        KnnWork& w = g_knn;
+        const int nby = (gy + KNN_BLK - 1) / KNN_BLK, nbx = (gx + KNN_BLK - 1) / KNN_BLK;
+        const int cap = std::min(c.n, KNN_CAND_CAP);
+        const size_t need = (size_t)nby * nbx * cap;
+        if (need > w.cand_elems) {
+            if (w.cand) cudaFree(w.cand);
+            w.cand = nullptr; w.cand_elems = 0;
+            TWXI_CUDA(cudaMalloc((void**)&w.cand, need * sizeof(int32_t)));
+            w.cand_elems = need;
+        }
+        if ((size_t)nby * nbx > w.cnt_elems) {
+            if (w.cnt) cudaFree(w.cnt);
+            w.cnt = nullptr; w.cnt_elems = 0;
+            TWXI_CUDA(cudaMalloc((void**)&w.cnt, (size_t)nby * nbx * sizeof(int32_t)));
+            w.cnt_elems = (size_t)nby * nbx;
+        }
+        a.cand_cap = cap; a.gx = gx; a.nbx = nbx;
+        const size_t smem_c = (size_t)c.n * 8 + 256 * 4;
+        TWXI_CUDA(cudaFuncSetAttribute(knn_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+        knn_candidates_kernel<<<nby * nbx, KNN_THREADS, smem_c, c.stream>>>(a, gy, w.cand, w.cnt);
+        TWXI_LAUNCH_CHECK();
+        a.cand = w.cand; a.cand_cnt = w.cnt;
+    }
     size_t smem = (size_t)c.n * 8 + KNN_SEL * 12 + 256 * 4;
     TWXI_CUDA(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     knn_kernel<<<npts, KNN_THREADS, smem, c.stream>>>(a);

@@ -74,6 +74,7 @@ struct ObsTable {
 // Query batch on the device (one variable).  q indexes points; all arrays sized for `cap` points.
 struct Batch {
     int npts = 0, cap = 0, k1 = 0, k1cap = 0, n_rm = 0, rm_zero = 0, ndays_cap = 0;
+    int gy = 0, gx = 0;            // > 0: the points are the cells of a gy x gx grid in row-major order (work chunk)
     double *lat = nullptr, *lon = nullptr, *elev = nullptr, *tdi = nullptr, *lst = nullptr;   // lst [cap][12]
     int32_t* rm_idx = nullptr;     // [cap][TWXI_MAX_RM]
     int32_t* idx = nullptr;        // [cap][k1]
@@ -104,7 +105,7 @@ struct Ctx {
 
 // ---- stage launchers (each enqueues on ctx.stream) ----------------------------------------------------
 int launch_knn(Ctx& c, int npts, const double* lat, const double* lon, const int32_t* rm_idx, int n_rm,
-               int rm_zero, int k1, int32_t* idx, double* dist, double* wgt, int32_t* status);
+               int rm_zero, int k1, int32_t* idx, double* dist, double* wgt, int32_t* status, int gy = 0, int gx = 0);
 int launch_nngh_params(Ctx& c, Batch& b, const int32_t* norm_override, const int32_t* anom_override, int only_mth,
                        int need_norm, int need_anom, int need_vario);
 int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override);
@@ -182,5 +183,105 @@ __device__ __forceinline__ double gcdist_sp(double lon1, double lat1, double lon
     double H2 = (3 * R + 1) / (2 * S);
     return D * (1 + f * H1 * sinF2 * cosG2 - f * H2 * cosF2 * sinG2);
 }
+
+// ---- FP64 tensor-pipe helpers shared by the kriging and GWR kernels ----------------------------------------------------
+// mma.sync.m8n8k4.f64 ("DMMA").  C fragment: lane = 4*row + col/2 holds two adjacent columns.
+__device__ __forceinline__ void dmma(double2& c, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c.x), "+d"(c.y) : "d"(a), "d"(b));
+}
+// c += X * Y' for two 8x8 tiles in C-fragment layout (even columns, then odd columns)
+__device__ __forceinline__ void dmma2(double2& c, const double2& x, const double2& y) {
+    dmma(c, x.x, y.x);
+    dmma(c, x.y, y.y);
+}
+
+// 1/d for a normal positive double without the slow-path branches of the IEEE division: MUFU seed (~2^-20) and one
+// third-order Newton step (error ~ e^3, below 1 ulp).  Non-positive / non-finite pivots are rejected by the caller.
+__device__ __forceinline__ double fast_rcp(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    const double e = fma(-d, r, 1.0);
+    const double e2 = fma(e, e, e);
+    return fma(r, e2, r);
+}
+
+// 1/sqrt(d) for a normal positive double: MUFU seed and one third-order step (error ~ e^3), like fast_rcp.
+__device__ __forceinline__ double fast_rsqrt(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double e = fma(-d * y, y, 1.0);
+    const double g = fma(e, 0.375, 0.5) * e;
+    return fma(y, g, y);
+}
+
+// Tensor-pipe form of the pivot-tile factorisation.  With the tile in C-fragment layout, lane (r, q = k/2) owns
+// M[r][k]; feeding that column (zero in the other lanes) as BOTH operands of one DMMA adds the outer product
+// M[:,k] M[:,k]' to every element at once: no column broadcasts and no predicates (finished rows and columns are exactly
+// zero and stay zero).  Fraction-free (Bareiss) scaling keeps the reciprocal off the serial pivot chain:
+//     M <- (d_k M - M[:,k] M[:,k]') / M(k-1)_(k-1,k-1),   d_k := M(k)_kk  (pivot of LDL' = d_k / previous d).
+// The inverse is accumulated TRANSPOSED, Z = inv(L)': Z[c][r] -= Z[c][k] m_rk needs column k of Z and the multipliers
+// m_rk = M[r][k] / d_k, both already sitting in the lanes (r, q = k/2) that feed the DMMA — no shuffles either.
+// Per pivot: one shuffle (d_k), two DMMAs, ~8 scalar FP64 ops; chain = shuffle + DMUL + DMMA.  The update of Z for
+// pivot k-1 is issued after the shuffle of pivot k so that it runs in the shuffle's shadow (in-order issue).
+// Returns Z scaled by the inverse square roots of the pivots (columns), i.e. the transpose of inv(chol(A)).
+template <int NPIV>
+__device__ __forceinline__ bool elim8_mma(double2& a, int lane) {
+    const int q = lane & 3;
+    bool ok = true;
+    double rprev = 1.0;                                       // 1 / d_(k-1)
+#pragma unroll
+    for (int k = 0; k < NPIV; ++k) {
+        const int kq = k >> 1;
+        const double mine = (k & 1) ? a.y : a.x;
+        const double e = (q == kq) ? mine : 0.0;              // M[r][k] in the lanes that own column k
+        const double dk = __shfl_sync(0xffffffffu, mine, 4 * k + kq);
+        const double ax = a.x * rprev, ay = a.y * rprev;      // in the shadow of the shuffle
+        ok = ok && (dk > 0.0);
+        const double es = -e * rprev;
+        double2 c = make_double2(dk * ax, dk * ay);           // M <- (d_k M - M[:,k] M[:,k]') / previous pivot
+        dmma(c, es, e);
+        a = c;
+        rprev = fast_rcp(dk);
+    }
+    a.x *= rprev; a.y *= rprev;                               // Schur complement of the first NPIV pivots
+    return ok;
+}
+
+// Returns Z = transpose of inv(chol(A)) in C-fragment layout (A = the SPD tile `a`).  The seven Z updates depend on
+// each other only through Z, so the scheduler is free to run them behind the pivot chain.
+__device__ __forceinline__ bool chol8_inverse_t(double2 a, double2& z, int lane) {
+    const int r = lane >> 2, q = lane & 3;
+    z.x = (2 * q == r) ? 1.0 : 0.0;
+    z.y = (2 * q + 1 == r) ? 1.0 : 0.0;
+    bool ok = true;
+    double dx = 1.0, dy = 1.0;                                // LDL' pivots of columns 2q, 2q+1 (scale the columns of Z)
+    double rprev = 1.0;                                       // 1 / d_(k-1)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int kq = k >> 1;
+        const double mine = (k & 1) ? a.y : a.x;
+        const double e = (q == kq) ? mine : 0.0;              // M[r][k] in the lanes that own column k
+        const double dk = __shfl_sync(0xffffffffu, mine, 4 * k + kq);
+        const double ax = a.x * rprev, ay = a.y * rprev;      // in the shadow of the shuffle
+        ok = ok && (dk > 0.0);
+        const double piv = dk * rprev;
+        if (kq == q) { if (k & 1) dy = piv; else dx = piv; }
+        if (k < 7) {
+            const double es = -e * rprev;
+            double2 c = make_double2(dk * ax, dk * ay);       // M <- (d_k M - M[:,k] M[:,k]') / previous pivot
+            dmma(c, es, e);
+            a = c;
+            const double p = fast_rcp(dk);
+            const double mneg = (r == k) ? 0.0 : -e * p;      // Z[c][r] -= Z[c][k] m_rk
+            dmma(z, (k & 1) ? z.y : z.x, mneg);
+            rprev = p;
+        }
+    }
+    z.x *= fast_rsqrt(dx);
+    z.y *= fast_rsqrt(dy);
+    return ok;
+}
+
 
 }  // namespace twxi

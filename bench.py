@@ -278,11 +278,15 @@ def main():
     achieved = flops / (krig_ms / 1e3) / 1e12 if krig_ms > 0 else None
     roofline = {"bound": "tensor", "kernel": "ked_kernel (regression kriging, FP64 DMMA m8n8k4)",
                 "achieved": achieved, "peak": dmma.value, "unit": "TFLOP/s",
-                "frac": (achieved / dmma.value) if achieved else None, "traffic": None,
+                "frac": (achieved / dmma.value) if achieved else None, "traffic": _ked_traffic(),
                 "peak_source": "FP64 tensor (DMMA) peak measured in this run by twxi_measure_fp64_peak; "
                                "MEASURED_PEAKS.json has no FP64 entry (nominal B200 FP64: 37-40 TFLOP/s)",
                 "fp64_dfma_peak_tflops": dfma.value,
-                "algorithmic_flops_per_step": flops, "launches_per_step": 2, "ms_per_step_kernel": krig_ms,
+                "algorithmic_flops_per_step": flops,
+                "launches_per_step": "2 variable passes x one launch per size class NB = ceil(n/8)",
+                "traffic_note": "DRAM bytes (read+write) of all ked_kernel launches of one step, from the committed ncu "
+                                "capture profiles/ked_traffic_r01.json",
+                "ms_per_step_kernel": krig_ms,
                 "stage_ms": dict(zip(["knn", "nngh_params", "krig", "gwr_daily", "fixer_quantise"],
                                      [round(float(x), 3) for x in stage_ms])),
                 "hbm_floor": {"bytes_per_cell_day": 4, "achieved_gbs": units * 4 / (tot_ms / args.steps / 1e3) / 1e9,
@@ -304,6 +308,15 @@ def main():
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def _ked_traffic():
+    try:
+        with open(os.path.join(ROOT, "profiles", "ked_traffic_r01.json")) as f:
+            d = json.load(f)
+        return d["dram_bytes_read"] + d["dram_bytes_write"]
+    except Exception:
+        return None
 
 
 def _measured(key):

@@ -219,3 +219,49 @@ def test_interp_chunk_vs_oracle(env):
         assert np.abs(out[k][:, good] - ref[k][:, good]).max() < TOL_C
         assert out[k][0, 0, 0] == ref[k][0, 0, 0]                     # fill value
     assert np.array_equal(out["ninvalid"], ref["ninvalid"])
+
+
+def test_conus_scale_station_table():
+    """BASELINE configs 3-5 use ~10 000 stations over CONUS: the neighbour search scans / prunes a 5x larger table,
+    the station-station distance table is 800 MB, and land/ocean mask plus out-of-domain stations (NaN optim /
+    variogram columns) come into play.  A chunk in the interior and a leave-one-out batch against the oracle."""
+    from topowx_b200 import synth, db
+    from topowx_b200.context import TwxiContext, interp_chunk
+    f = synth.Fields()
+    days = synth.make_days(1995, 1)
+    da = [synth.make_station_db(w, 10000, synth.conus_bbox(), f, days) for w in (0, 1)]
+    oda = [o.StationDb(d.stns, d.var, d.days) for d in da]
+    ctx = [TwxiContext(d, np.isnan(d.stns[db.BAD])) for d in da]
+    wrk = synth.make_wrk_chk(f, 1500, 3400, 30, 40)
+    out = interp_chunk(ctx[0], ctx[1], wrk)
+    pti = o.PtInterpTair(oda[0], oda[1])
+    land = np.argwhere(wrk[2] != 0)
+    assert land.size > 0
+    r = np.random.default_rng(5)
+    cells = [tuple(int(v) for v in land[i]) for i in r.choice(len(land), min(5, len(land)), replace=False)]
+    ref = o.interp_chunk(pti, wrk, cells=cells)
+    for (a, b) in cells:
+        assert out["status"][a, b] == ref["status"][a, b]
+        if ref["status"][a, b] != 0:
+            continue
+        for k in ("tmin", "tmax"):
+            assert np.abs(out[k][:, a, b].astype(int) - ref[k][:, a, b].astype(int)).max() <= 1
+        for k in ("tmin_norm", "tmax_norm", "tmin_se", "tmax_se"):
+            assert np.abs(out[k][:, a, b] - ref[k][:, a, b]).max() < TOL_C
+    # step24-style LOO at 4 in-domain stations of the tmax DB
+    w = 1
+    xv = o.XvalTairOverall(oda[w])
+    cand = np.nonzero(np.isnan(da[w].stns[db.BAD]) & np.isfinite(da[w].stns[db.MASK]))[0]
+    sel = cand[r.choice(cand.size, 4, replace=False)]
+    s = da[w].stns[sel]
+    lst = np.stack([s[db.get_lst_varname(m)] for m in range(1, 13)], axis=1)
+    rm = ctx[w].local_of_db[sel].astype(np.int32).reshape(-1, 1)
+    dly, norms, se, var, st = ctx[w].interp_points(s[db.LAT], s[db.LON], s[db.ELEV], s[db.TDI], lst, rm_idx=rm, rm_zero=True)
+    for i, sid in enumerate(s[db.STN_ID]):
+        try:
+            od, on, ose = xv.run_interp(sid)
+        except o.OracleError as e:
+            assert st[i] == e.status
+            continue
+        assert st[i] == 0
+        assert np.abs(on - norms[i]).max() < TOL_C and np.abs(od - dly[i]).max() < TOL_C

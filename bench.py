@@ -6,8 +6,8 @@
 Workload at N=1 = BASELINE.json configs[1]: one 250x250 30-arcsec tile, one year (365 days) of daily Tmin+Tmax
 (monthly-normal regression kriging + daily-anomaly GWR + Tmin>=Tmax fixer + int16 quantisation), ~2000 synthetic
 stations per variable + DEM/TDI/LST predictors.  One step = the whole tile once through twxi_interp_chunk.
-With --gpus N (torchrun) every rank processes its own tile (weak scaling; stations replicated per rank, no
-collective on the data path).  Prints ONE JSON line on rank 0.
+With --gpus N (torchrun) every rank processes its own replica of that tile (weak scaling with identical work per
+GPU; stations replicated per rank, no collective on the data path).  Prints ONE JSON line on rank 0.
 """
 import argparse
 import ctypes as C
@@ -34,9 +34,13 @@ def build_inputs(rank):
     from topowx_b200 import synth
     f = synth.Fields()
     days = synth.make_days(1995, 1)
-    col0 = synth.TILE_COL0 + rank * TILE          # each rank owns a different tile of the same tile row
+    # weak scaling: every rank owns one tile with the SAME amount of work (a replica of the benchmark tile and of its
+    # station set), so that max-over-ranks time measures the machine, not the tile-to-tile spread of neighbour counts
+    # (in a CONUS run each GPU works through ~45 tiles and that spread averages out, topowx_b200/interp/tiling.py)
+    del rank
+    col0 = synth.TILE_COL0
     bbox = synth.tile_bbox(col0=col0)
-    da = [synth.make_station_db(w, NSTNS, bbox, f, days, seed=synth.SEED_STNS + 17 * rank) for w in (0, 1)]
+    da = [synth.make_station_db(w, NSTNS, bbox, f, days, seed=synth.SEED_STNS) for w in (0, 1)]
     wrk = synth.make_wrk_chk(f, synth.TILE_ROW0, col0, TILE, TILE)
     return da, wrk
 

@@ -174,7 +174,22 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(KnnArgs a) {
         }
     }
     __syncthreads();
-    bitonic_sort(selkey, selidx, P);
+    if (count_le <= (unsigned)KNN_THREADS) {
+        // rank by counting: every survivor counts the survivors that precede it in (key, index) order — no barriers,
+        // broadcast shared-memory reads; pairs are distinct, so the ranks are a permutation
+        unsigned long long mk = 0ull;
+        int mi = 0, rank = 0;
+        const bool have = tid < (int)count_le;
+        if (have) {
+            mk = selkey[tid]; mi = selidx[tid];
+            for (int j = 0; j < (int)count_le; ++j) rank += pair_less(selkey[j], selidx[j], mk, mi) ? 1 : 0;
+        }
+        __syncthreads();
+        if (have) { selkey[rank] = mk; selidx[rank] = mi; }
+        __syncthreads();
+    } else {
+        bitonic_sort(selkey, selidx, P);
+    }
 
     // ---- phase 4: kilometres for the k1 survivors; verify (km, index) order ---------------------------
     int bad = 0;

@@ -498,3 +498,31 @@ class XvalTairOverall(object):
     def run_interp(self, stn_id, norms_only=False):                # :579-604
         xval_stn = self.stn_da.stns[self.stn_da.stn_idxs[stn_id]].copy()
         return self.interp_tair.interp(xval_stn, stn_id, norms_only=norms_only)
+
+
+class XvalTairAnom(object):
+    """optimize.py:477-545: cross validation of the GWR neighbour count at one station."""
+
+    def __init__(self, stn_da):
+        mask_stns = np.isnan(stn_da.stns[BAD])                     # :497
+        ss = StationSelect(stn_da, stn_mask=mask_stns, rm_zero_dist_stns=True)     # :499
+        self.stn_da = stn_da
+        self.gwr = GwrTairAnom(ss)
+
+    def run_xval(self, stn_id, a_nnghs):                           # :505-545
+        xval_stn = self.stn_da.stns[self.stn_da.stn_idxs[stn_id]]
+        xval_obs = self.stn_da.load_obs(np.array([stn_id]))[:, 0].astype(np.float64)
+        a_nnghs = np.asarray(a_nnghs)
+        bias = np.zeros((a_nnghs.size, 12))
+        mae, r2 = bias.copy(), bias.copy()
+        for x, nnghs in enumerate(a_nnghs):
+            for mth in range(1, 13):
+                xval_anom = xval_obs[self.stn_da.mth_idx[mth]] - xval_stn[norm_name(mth)]
+                interp_tair = self.gwr.gwr_mth(xval_stn, mth, int(nnghs), stns_rm=stn_id)
+                interp_anom = interp_tair - xval_stn[norm_name(mth)]
+                difs = interp_anom - xval_anom
+                bias[x, mth - 1] = np.mean(difs)
+                mae[x, mth - 1] = np.mean(np.abs(difs))
+                r_value = np.corrcoef(interp_anom, xval_anom)[0, 1]      # = stats.linregress(...)[2] (:530)
+                r2[x, mth - 1] = r_value ** 2
+        return bias, mae, r2

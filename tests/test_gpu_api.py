@@ -238,3 +238,25 @@ def test_grid_knn_candidate_pruning_is_exact(env, monkeypatch):
     assert (pruned["status"] == 255).sum() == 4 * 83 + 60 - 4
     for k in ("tmin", "tmax", "tmin_norm", "tmax_norm", "tmin_se", "tmax_se", "ninvalid", "status"):
         assert np.array_equal(pruned[k], full[k]), k
+
+
+def test_xval_tair_anom_class(env):
+    """XvalTairAnom (optimize.py:477-545, the step23 driver): leave-one-out GWR at a station for a set of neighbour
+    counts -> bias / MAE / r2 per (count, month); GPU mirror (single and batch form) against the oracle."""
+    from topowx_b200 import interp as twx_interp
+    db = env["db"]
+    w = 0
+    da, oda = env["da"][w], env["oda"][w]
+    xv_gpu = twx_interp.XvalTairAnom(da, "tmin")
+    xv_ref = o.XvalTairAnom(oda)
+    cand = np.nonzero(np.isnan(da.stns[db.BAD]) & np.isfinite(da.stns[db.MASK]))[0]
+    ids = da.stns[db.STN_ID][cand[np.random.default_rng(21).choice(cand.size, 3, replace=False)]]
+    a_nnghs = np.array([35, 63, 147])
+    bias, mae, r2, st = xv_gpu.run_xval_batch(ids, a_nnghs)
+    assert np.all(st == 0)
+    for i, sid in enumerate(ids):
+        rb, rm_, rr = xv_ref.run_xval(sid, a_nnghs)
+        assert np.abs(bias[i] - rb).max() < 1e-6 and np.abs(mae[i] - rm_).max() < 1e-6
+        assert np.abs(r2[i] - rr).max() < 1e-8
+    b1, m1, r1 = xv_gpu.run_xval(ids[0], a_nnghs)                  # reference signature
+    assert np.array_equal(b1, bias[0]) and np.array_equal(m1, mae[0]) and np.array_equal(r1, r2[0])

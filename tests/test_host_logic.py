@@ -91,3 +91,29 @@ def test_tiler_skips_empty_tiles_and_partitions():
 def test_tiler_rejects_bad_sizes():
     with pytest.raises(ValueError):
         Tiler(dict(mask=np.ones((20, 30), bool), lon=np.arange(30.), lat=np.arange(20.)), [], 7, 10, 5, 5)
+
+
+def test_oracle_xval_tair_anom_is_gwr_mth_statistics(small_db):
+    """oracle.XvalTairAnom (optimize.py:505-545) is bias / MAE / r2 of GwrTairAnom.gwr_mth minus the held-out station's
+    own anomalies; check it against a direct evaluation for one station and one neighbour count."""
+    from oracle import twx_oracle as o
+    from topowx_b200 import db
+    oda = o.StationDb(small_db.stns, small_db.var, small_db.days)
+    xv = o.XvalTairAnom(oda)
+    good = np.nonzero(np.isnan(small_db.stns[db.BAD]) & np.isfinite(small_db.stns[db.MASK]))[0]
+    sid = small_db.stns[db.STN_ID][good[7]]
+    bias, mae, r2 = xv.run_xval(sid, np.array([40]))
+    stn = oda.stns[oda.stn_idxs[sid]]
+    for mth in (1, 7):
+        obs = oda.load_obs(np.array([sid]))[:, 0].astype(np.float64)[oda.mth_idx[mth]]
+        pred = xv.gwr.gwr_mth(stn, mth, 40, stns_rm=sid)
+        assert abs(bias[0, mth - 1] - np.mean(pred - obs)) < 1e-12
+        assert abs(mae[0, mth - 1] - np.mean(np.abs(pred - obs))) < 1e-12
+        assert 0.0 <= r2[0, mth - 1] <= 1.0
+
+
+def test_build_nstn_bandwidths_matches_reference_set():
+    """optimize.py:376-405 evaluated at the arguments of steps 21 and 23."""
+    from topowx_b200.interp import build_nstn_bandwidths
+    assert build_nstn_bandwidths(35, 150, 0.10).tolist() == [35, 39, 43, 47, 52, 57, 63, 69, 76, 84, 92, 101, 111, 122,
+                                                             134, 147]

@@ -69,3 +69,21 @@ for k, (s, n, src) in sorted(lines.items(), key=lambda kv: -kv[1][0])[:22]:
 print("-- top lines by instructions")
 for k, (s, n, src) in sorted(lines.items(), key=lambda kv: -kv[1][1])[:14]:
     print("%-10s %4d smp %5.1f%% inst %5.1f%%  %s" % (k[0][:10], k[1], 100 * s / max(ts, 1), 100 * n / max(ti, 1), src.strip()))
+if len(sys.argv) > 4:      # optional: "file:lo-hi=name,..." groups -> share of samples / instructions per group
+    groups = []
+    for g in sys.argv[4].split(","):
+        rng_, name = g.split("=")
+        f, lh = rng_.split(":")
+        lo, hi = lh.split("-")
+        groups.append((f, int(lo), int(hi), name))
+    agg = collections.defaultdict(lambda: [0, 0])
+    for k, (s, n, src) in lines.items():
+        name = "other"
+        for f, lo, hi, nm in groups:
+            if k[0].startswith(f) and lo <= k[1] <= hi:
+                name = nm
+                break
+        agg[name][0] += s; agg[name][1] += n
+    print("-- groups")
+    for nm, (s, n) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print("%-14s smp %5.1f%% inst %5.1f%%" % (nm, 100 * s / max(ts, 1), 100 * n / max(ti, 1)))

@@ -578,7 +578,314 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
     if (warp == NW && pending) ked_finish(a.mean, a.var, a.status, pend_S, pend_q, pend_m, pend_yref, pend_c00, lane);
 }
 
+// ---- 3b. one warp per problem (v5) ------------------------------------------------------------------------------------
+// The same left-looking tile algorithm executed by ONE warp per problem (one-warp CTAs): no CTA barriers, no work duplicated
+// between warps, and the instruction-level parallelism comes from register blocking (a group of up to KW_R tile rows shares
+// every L(c,J) operand) instead of from warps that wait for each other.  All tile slots are lane-private (C-fragment
+// layout in, C-fragment layout out), so the stage loop needs a __syncwarp only around the transposition of -inv(L_KK).
+// Stage K (pivot tile D_K in registers, column c = K+1):
+//   phase P  N(I,c) += sum_{J<K} L(I,J) L(c,J)'  for the rows I > c, and the same sum for the next pivot tile; none of it
+//            depends on D_K, so the serial pivot chain of D_K (chol8 steps, ~110 cycles each) is dealt out one step per
+//            J iteration and runs in the shadow of the DMMA stream;
+//   phase F  -W = -inv(L_KK)';  L(c,K) = N(c,K)(-W)';  D_{K+1} = -(N_diag + L(c,K)L(c,K)');
+//            rows I > c:  L(I,K) = N(I,K)(-W)', N(I,c) += L(I,K)L(c,K)'.
+// Tile row c is dead after stage K, so the distance tiles of the warp's NEXT problem (same size class, same slots) are
+// fetched into it right away with a TMA bulk copy: the loads of problem i+1 hide behind the stages of problem i with no
+// second buffer.
+constexpr int KW_HDR = 8 + 32 + 64;     // doubles: mbarrier, 2^(j/32), -inv(L_KK) transposition buffer
+constexpr int KW_R = 4;                 // tile rows per register-blocked group
+
+struct WChain {
+    double2 a, z;
+    double dx, dy, rprev;
+    bool ok;
+};
+__device__ __forceinline__ void wchain_init(WChain& c, double2 D, int lane) {
+    const int r = lane >> 2, q = lane & 3;
+    c.a = D;
+    c.z.x = (2 * q == r) ? 1.0 : 0.0;
+    c.z.y = (2 * q + 1 == r) ? 1.0 : 0.0;
+    c.dx = 1.0; c.dy = 1.0; c.rprev = 1.0; c.ok = true;
+}
+// pivot k of chol8_inverse_t (twxi_internal.cuh) with a run-time k
+__device__ __forceinline__ void wchain_step(WChain& c, int k, int lane) {
+    const int r = lane >> 2, q = lane & 3, kq = k >> 1;
+    const bool odd = k & 1;
+    const double mine = odd ? c.a.y : c.a.x;
+    const double e = (q == kq) ? mine : 0.0;
+    const double dk = __shfl_sync(0xffffffffu, mine, 4 * k + kq);
+    const double ax = c.a.x * c.rprev, ay = c.a.y * c.rprev;
+    c.ok = c.ok && (dk > 0.0);
+    const double piv = dk * c.rprev;
+    if (kq == q) { if (odd) c.dy = piv; else c.dx = piv; }
+    if (k < 7) {
+        const double es = -e * c.rprev;
+        double2 t = make_double2(dk * ax, dk * ay);
+        dmma(t, es, e);
+        c.a = t;
+        const double p = fast_rcp(dk);
+        const double mneg = (r == k) ? 0.0 : -e * p;
+        dmma(c.z, odd ? c.z.y : c.z.x, mneg);
+        c.rprev = p;
+    }
+}
+
+// phase P for RR rows I0.. (all > c); DIAG: also the pivot tile of column c (accD)
+template <int RR, bool DIAG>
+__device__ __forceinline__ void kw_partial(double2* tl2, int c, int K, int I0, double2& accD, WChain& ch, int& ks, int lane) {
+    const double2* pB = tl2 + ltile(c, 0) * 32;
+    const double2* pA[RR > 0 ? RR : 1];
+    double2 acc[RR > 0 ? RR : 1], av[RR > 0 ? RR : 1];
+#pragma unroll
+    for (int r = 0; r < RR; ++r) {
+        pA[r] = tl2 + ltile(I0 + r, 0) * 32;
+        acc[r] = pA[r][c * 32];
+        av[r] = pA[r][0];
+    }
+    double2 b = pB[0];
+    for (int J = 0; J < K; ++J) {
+        const double2 bc = b;
+        double2 ac[RR > 0 ? RR : 1];
+#pragma unroll
+        for (int r = 0; r < RR; ++r) ac[r] = av[r];
+        b = pB[(J + 1) * 32];                                 // slot (c, K) at the last iteration: valid memory, unused
+#pragma unroll
+        for (int r = 0; r < RR; ++r) av[r] = pA[r][(J + 1) * 32];
+        if (DIAG) dmma(accD, bc.x, bc.x);
+#pragma unroll
+        for (int r = 0; r < RR; ++r) dmma(acc[r], ac[r].x, bc.x);
+        if (DIAG) dmma(accD, bc.y, bc.y);
+#pragma unroll
+        for (int r = 0; r < RR; ++r) dmma(acc[r], ac[r].y, bc.y);
+        if (ks < 8) { wchain_step(ch, ks, lane); ++ks; }
+    }
+#pragma unroll
+    for (int r = 0; r < RR; ++r) tl2[(ltile(I0 + r, 0) + c) * 32] = acc[r];
+}
+
+// phase F for RR rows I0.. (all > c)
+template <int RR>
+__device__ __forceinline__ void kw_finish(double2* tl2, int c, int K, int I0, const double2 negW, const double2 lk1) {
+    double2 nv[RR], acc[RR], l[RR];
+    int base[RR];
+#pragma unroll
+    for (int r = 0; r < RR; ++r) {
+        base[r] = ltile(I0 + r, 0) * 32;
+        nv[r] = tl2[base[r] + K * 32];
+        acc[r] = tl2[base[r] + c * 32];
+        l[r] = make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int r = 0; r < RR; ++r) dmma(l[r], nv[r].x, negW.x);
+#pragma unroll
+    for (int r = 0; r < RR; ++r) dmma(l[r], nv[r].y, negW.y);
+#pragma unroll
+    for (int r = 0; r < RR; ++r) tl2[base[r] + K * 32] = l[r];
+#pragma unroll
+    for (int r = 0; r < RR; ++r) dmma(acc[r], l[r].x, lk1.x);
+#pragma unroll
+    for (int r = 0; r < RR; ++r) dmma(acc[r], l[r].y, lk1.y);
+#pragma unroll
+    for (int r = 0; r < RR; ++r) tl2[base[r] + c * 32] = acc[r];
+}
+
+template <int MINB, int NMAX>
+__global__ void __launch_bounds__(32, MINB) ked_warp_kernel(KedArgs a) {
+    extern __shared__ __align__(16) double sm[];
+    void* mbar = sm;                                          // mbarrier of the distance-tile bulk copies
+    double* tab32 = sm + 8;                                   // 32: 2^(j/32)
+    double* Wd = sm + 40;                                     // 64: -inv(L_KK), row-major
+    double* tiles = sm + KW_HDR;
+    constexpr int NJ = (NMAX + 31) / 32;                      // stations per lane in the B' build (n <= NMAX)
+
+    const int lane = threadIdx.x;
+    const int NB = a.nbv;
+    const int count = a.bcount[NB], start = a.bstart[NB];
+    const int N = a.st.n;
+    const int r8 = lane >> 2, q4 = lane & 3;
+    int slot = blockIdx.x;
+    if (slot >= count) return;
+    tab32[lane] = exp2((double)lane / 32.0);
+    if (lane == 0) mbar_init(mbar, 1);
+    __syncwarp();
+    uint32_t parity = 0;
+    double2* const tl2 = reinterpret_cast<double2*>(tiles) + lane;
+    const uint32_t tx_bytes = (uint32_t)(NB * (NB - 1) / 2) * 512u;     // tile rows 1..NB-1, I tiles each
+
+    int2 desc = a.list[start + slot];
+    int2 desc_next = slot + (int)gridDim.x < count ? a.list[start + slot + gridDim.x] : make_int2(0, 0);
+    int sj[NJ], s_first;
+    {
+        const int32_t* ip = a.idx + (size_t)(desc.x / 12) * a.k1;
+        s_first = ip[0];
+#pragma unroll
+        for (int t = 0; t < NJ; ++t) sj[t] = (lane + t * 32 < desc.y) ? ip[lane + t * 32] : 0;
+    }
+    if (lane == 0 && tx_bytes) {                              // distance tiles of the first problem
+        const double* hc = a.hc + (size_t)(desc.x / 12 - a.q0) * a.hc_stride;
+        mbar_expect_tx(mbar, tx_bytes);
+        for (int I = 1; I < NB; ++I) bulk_g2s(tiles + ltile(I, 0) * 64, hc + htile(I, 0) * 64, (uint32_t)I * 512u, mbar);
+    }
+    for (; slot < count; slot += gridDim.x) {
+        const int pid = desc.x, n = desc.y;
+        const int q = pid / 12, m = pid - q * 12;
+        const bool has_next = slot + (int)gridDim.x < count;
+        const double2* hc2 = reinterpret_cast<const double2*>(a.hc + (size_t)(q - a.q0) * a.hc_stride) + lane;
+        // ---- gathers of the augmented rows (one station per lane and pass; indices prefetched during the previous problem)
+        const double* lstm = a.st.lst + (size_t)m * N;
+        const double* normm = a.st.norm + (size_t)m * N;
+        const double yref = normm[s_first];
+        double gl[NJ][6];
+#pragma unroll
+        for (int t = 0; t < NJ; ++t) {
+            const int j = lane + t * 32;
+            if (j < n) {
+                const int s = sj[t];
+                gl[t][0] = a.st.lon[s]; gl[t][1] = a.st.lat[s]; gl[t][2] = a.st.elev[s];
+                gl[t][3] = lstm[s]; gl[t][4] = normm[s]; gl[t][5] = a.h0[(size_t)q * a.k1 + j];
+            }
+        }
+        const double* vp = a.vario_is_override ? a.vario + (size_t)q * 3 : a.vario + ((size_t)q * 12 + m) * 3;
+        const double nug = vp[0], psill = vp[1], rng = vp[2];
+        const double lon0 = a.qlon[q], lat0 = a.qlat[q], elev0 = a.qelev[q], lst0 = a.qlst[(size_t)q * 12 + m];
+        const double2 hd0 = hc2[0];                           // raw distances of the diagonal tiles 0 and 1
+        double2 hdn = NB > 1 ? hc2[htile(1, 1) * 32] : make_double2(0.0, 0.0);
+        CovPar cp;
+        cp.c00 = nug + psill;
+        cp.psill_eff = rng != 0.0 ? psill : 0.0;              // range == 0: pure nugget model (interp.R:223-227)
+        cp.nir = rng != 0.0 ? -1.0 / rng : 0.0;
+        // prefetch: descriptor two problems ahead, neighbour indices of the next problem
+        desc = desc_next;
+        if (slot + 2 * (int)gridDim.x < count) desc_next = a.list[start + slot + 2 * gridDim.x];
+        const double* hc_next = a.hc;
+        if (has_next) {
+            const int32_t* ip = a.idx + (size_t)(desc.x / 12) * a.k1;
+            hc_next = a.hc + (size_t)(desc.x / 12 - a.q0) * a.hc_stride;
+            s_first = ip[0];
+#pragma unroll
+            for (int t = 0; t < NJ; ++t) sj[t] = (lane + t * 32 < desc.y) ? ip[lane + t * 32] : 0;
+        }
+        if (tx_bytes) mbar_wait(mbar, parity);                // distance tiles have landed in their slots
+        parity ^= 1u;
+        // ---- covariances in place: slot <- -C(h).  Rows 1..NB-2 need no masking; four tiles per pass
+        {
+            const int T0 = NB >= 2 ? ltile(NB - 1, 0) : 0;
+            int t = 0;
+            for (; t + 3 < T0; t += 4) {
+                const double2 h1 = tl2[t * 32], h2 = tl2[(t + 1) * 32], h3 = tl2[(t + 2) * 32], h4 = tl2[(t + 3) * 32];
+                double2 v1, v2, v3, v4;
+                v1.x = -cov(h1.x, cp, tab32); v2.x = -cov(h2.x, cp, tab32); v3.x = -cov(h3.x, cp, tab32); v4.x = -cov(h4.x, cp, tab32);
+                v1.y = -cov(h1.y, cp, tab32); v2.y = -cov(h2.y, cp, tab32); v3.y = -cov(h3.y, cp, tab32); v4.y = -cov(h4.y, cp, tab32);
+                tl2[t * 32] = v1; tl2[(t + 1) * 32] = v2; tl2[(t + 2) * 32] = v3; tl2[(t + 3) * 32] = v4;
+            }
+            for (; t < T0; ++t) {
+                const double2 h1 = tl2[t * 32];
+                tl2[t * 32] = make_double2(-cov(h1.x, cp, tab32), -cov(h1.y, cp, tab32));
+            }
+            const bool plain = 8 * NB <= n;                   // last row of V: identity padding beyond n
+            for (int c = 0; c < NB - 1; ++c) {
+                const double2 v = cov_tile(tl2[(T0 + c) * 32], 8 * (NB - 1) + r8, 8 * c + 2 * q4, n, cp, tab32, plain);
+                tl2[(T0 + c) * 32] = make_double2(-v.x, -v.y);
+            }
+        }
+        // ---- augmented rows -B' = -[1, dlon, dlat, delev, dlst, y - yref, c0]' into tile row NB
+        {
+            double* row = tiles + ltile(NB, 0) * 64;
+#pragma unroll
+            for (int t = 0; t < NJ; ++t) {
+                const int j = lane + t * 32;
+                if (j < 8 * NB) {
+                    double* col = row + (j >> 3) * 64 + (j & 7);
+                    const bool in = j < n;
+                    col[0] = in ? -1.0 : 0.0;
+                    col[8] = in ? lon0 - gl[t][0] : 0.0;
+                    col[16] = in ? lat0 - gl[t][1] : 0.0;
+                    col[24] = in ? (elev0 - gl[t][2]) * 1e-3 : 0.0;
+                    col[32] = in ? (lst0 - gl[t][3]) * 0.1 : 0.0;
+                    col[40] = in ? yref - gl[t][4] : 0.0;
+                    col[48] = in ? -cov(gl[t][5], cp, tab32) : 0.0;
+                    col[56] = 0.0;
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0 && has_next && tx_bytes) mbar_expect_tx(mbar, tx_bytes);   // armed for the next problem's rows
+
+        // ---- stage loop
+        double2 D = cov_tile(hd0, r8, 2 * q4, n, cp, tab32, false);     // V(0,0)
+        bool singular = false;
+        int next_row = 1;                                     // next tile row of the following problem to fetch
+        for (int K = 0; K < NB; ++K) {
+            const int c = K + 1;
+            double2 accD = make_double2(0.0, 0.0);            // -V(c,c); zero for the S tile (c == NB)
+            if (c < NB) {
+                const double2 v = cov_tile(hdn, 8 * c + r8, 8 * c + 2 * q4, n, cp, tab32, false);
+                accD = make_double2(-v.x, -v.y);
+            }
+            if (c + 1 < NB) hdn = hc2[htile(c + 1, c + 1) * 32];
+            WChain ch;
+            wchain_init(ch, D, lane);
+            int ks = 0;
+            const int mrows = NB - c;                         // rows below c (the B' row included)
+            if (K > 0) {
+                int I0 = c + 1, left = mrows;
+                if (left >= 4) { kw_partial<4, true>(tl2, c, K, I0, accD, ch, ks, lane); I0 += 4; left -= 4; }
+                else if (left == 3) { kw_partial<3, true>(tl2, c, K, I0, accD, ch, ks, lane); left = 0; }
+                else if (left == 2) { kw_partial<2, true>(tl2, c, K, I0, accD, ch, ks, lane); left = 0; }
+                else if (left == 1) { kw_partial<1, true>(tl2, c, K, I0, accD, ch, ks, lane); left = 0; }
+                else { kw_partial<0, true>(tl2, c, K, I0, accD, ch, ks, lane); }
+                for (; left >= 4; left -= 4, I0 += 4) kw_partial<4, false>(tl2, c, K, I0, accD, ch, ks, lane);
+                if (left == 3) kw_partial<3, false>(tl2, c, K, I0, accD, ch, ks, lane);
+                else if (left == 2) kw_partial<2, false>(tl2, c, K, I0, accD, ch, ks, lane);
+                else if (left == 1) kw_partial<1, false>(tl2, c, K, I0, accD, ch, ks, lane);
+            }
+            while (ks < 8) { wchain_step(ch, ks, lane); ++ks; }
+            if (!ch.ok) { singular = true; break; }
+            Wd[16 * q4 + r8] = -ch.z.x * fast_rsqrt(ch.dx);   // lane (c, q) holds Z[c][2q..2q+1] = W[2q..2q+1][c]
+            Wd[16 * q4 + 8 + r8] = -ch.z.y * fast_rsqrt(ch.dy);
+            __syncwarp();
+            const double2 negW = reinterpret_cast<const double2*>(Wd)[lane];
+            __syncwarp();
+            double2 lk1 = make_double2(0.0, 0.0);
+            dmma2(lk1, tl2[(ltile(c, 0) + K) * 32], negW);    // L(c,K) = N(c,K) (-W)'
+            double2 nd = accD;
+            dmma2(nd, lk1, lk1);
+            D = make_double2(-nd.x, -nd.y);                   // D_{K+1}; -S after the last stage
+            {
+                int I0 = c + 1, left = mrows;
+                for (; left >= 4; left -= 4, I0 += 4) kw_finish<4>(tl2, c, K, I0, negW, lk1);
+                if (left == 3) kw_finish<3>(tl2, c, K, I0, negW, lk1);
+                else if (left == 2) kw_finish<2>(tl2, c, K, I0, negW, lk1);
+                else if (left == 1) kw_finish<1>(tl2, c, K, I0, negW, lk1);
+            }
+            if (has_next && c < NB) {                         // tile row c is dead: fetch it for the next problem
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    bulk_g2s(tiles + ltile(c, 0) * 64, hc_next + htile(c, 0) * 64, (uint32_t)c * 512u, mbar);
+                }
+                next_row = c + 1;
+            }
+        }
+        if (has_next && next_row < NB) {                      // singular problem: the remaining rows of the next one
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                for (int I = next_row; I < NB; ++I)
+                    bulk_g2s(tiles + ltile(I, 0) * 64, hc_next + htile(I, 0) * 64, (uint32_t)I * 512u, mbar);
+            }
+        }
+        if (singular) {
+            if (lane == 0) atomicCAS(a.status + q, TWXI_ST_OK, TWXI_ST_SINGULAR);
+        } else {
+            ked_finish(a.mean, a.var, a.status, make_double2(-D.x, -D.y), q, m, yref, cp.c00, lane);
+        }
+        __syncwarp();                                         // the B' row of the next problem overwrites tile row NB
+    }
+}
+
 static size_t ked_smem_for(int nbv) { return (size_t)(KED_HDR + (nbv * (nbv + 1) / 2) * 64) * sizeof(double); }
+static size_t kw_smem_for(int nbv) { return (size_t)(KW_HDR + (nbv * (nbv + 1) / 2) * 64) * sizeof(double); }
 
 struct KedWork {                 // device scratch of the kriging stage, owned per thread
     double* hc = nullptr;
@@ -587,7 +894,7 @@ struct KedWork {                 // device scratch of the kriging stage, owned p
     size_t list_cap = 0;
     int32_t* bins = nullptr;     // bcount | bstart | fill, each KED_MAXNB+1
     int sms = 0;
-    int occ[8][KED_MAXNB + 1];   // resident CTAs per SM for (variant, size class)
+    int occ[16][KED_MAXNB + 1];   // resident CTAs per SM for (variant, size class)
     int var_for[KED_MAXNB + 1];  // variant chosen for each size class
 };
 
@@ -605,6 +912,9 @@ static const KedVariant KED_VARIANTS[] = {
     {ked_kernel<3, 6, 128>, 3, 128},
     {ked_kernel<5, 4, 192>, 5, 192},
     {ked_kernel<7, 3, 255>, 7, 255},
+    {ked_warp_kernel<12, 96>, 0, 96},      // 6..8: one warp per problem (nw == 0)
+    {ked_warp_kernel<8, 128>, 0, 128},
+    {ked_warp_kernel<4, 192>, 0, 192},
 };
 constexpr int KED_NVARIANTS = sizeof(KED_VARIANTS) / sizeof(KED_VARIANTS[0]);
 static thread_local KedWork g_ked;
@@ -638,12 +948,13 @@ int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
             for (int v = 0; v < KED_NVARIANTS; ++v) {
                 int o = 0;
                 TWXI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, KED_VARIANTS[v].fn, (KED_VARIANTS[v].nw + 1) * 32,
-                                                                        ked_smem_for(nb)));
+                                                                        KED_VARIANTS[v].nw ? ked_smem_for(nb) : kw_smem_for(nb)));
                 w.occ[v][nb] = std::max(1, o);
             }
             int v = sel[nb - 1] - '0';
             if (v < 0 || v >= KED_NVARIANTS) v = KED_NVARIANTS - 1;
-            while (KED_VARIANTS[v].nmax < 8 * nb) ++v;        // the variant must cover n = 8 NB
+            while (KED_VARIANTS[v].nmax < 8 * nb && v + 1 < KED_NVARIANTS) ++v;   // the variant must cover n = 8 NB
+            if (KED_VARIANTS[v].nmax < 8 * nb) v = 5;
             w.var_for[nb] = v;
         }
         w.sms = p.multiProcessorCount;
@@ -693,8 +1004,8 @@ int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
         // largest classes first: they are the long poles
         for (int nbv = nbmax; nbv >= 1; --nbv) {
             a.nbv = nbv;
-            const size_t smem = ked_smem_for(nbv);
             const int v = w.var_for[nbv];
+            const size_t smem = KED_VARIANTS[v].nw ? ked_smem_for(nbv) : kw_smem_for(nbv);
             const int grid = std::min(w.sms * w.occ[v][nbv], std::max(1, nt));
             KED_VARIANTS[v].fn<<<grid, (KED_VARIANTS[v].nw + 1) * 32, smem, c.stream>>>(a);
             TWXI_LAUNCH_CHECK();

@@ -151,6 +151,60 @@ def test_krig_overrides_and_single_month(env):
         assert abs(om - mean[i, 0]) < TOL_C and abs(ov - var[i, 0]) <= TOL_VAR_REL * abs(ov)
 
 
+def test_krig_colocated_stations_are_singular():
+    """Two stations at the same location make the kriging covariance matrix singular: gstat stops, the drivers leave
+    the fill value (step25:154-160).  The library decides it exactly (a zero station-station distance inside the
+    point's neighbour set) instead of by the sign of a rounded pivot; points that do not see the pair are unaffected."""
+    from topowx_b200 import synth, db, _lib
+    from topowx_b200.context import TwxiContext
+    f = synth.Fields()
+    days = synth.make_days(1995, 1)
+    da = synth.make_station_db(1, 600, synth.tile_bbox(buf=2.0), f, days)
+    good = np.flatnonzero(np.isnan(da.stns[db.BAD]))
+    lon0, lat0 = synth.grid_lons(synth.TILE_COL0), synth.grid_lats(synth.TILE_ROW0)
+    d = o.grt_circle_dist(lon0, lat0, da.stns[db.LON][good], da.stns[db.LAT][good])
+    a, b = good[np.argsort(d)[:2]]                        # the two stations nearest the tile's first cell
+    da.stns[db.LON][b], da.stns[db.LAT][b] = da.stns[db.LON][a], da.stns[db.LAT][a]
+    ctx = TwxiContext(da, np.isnan(da.stns[db.BAD]))
+    oda = o.StationDb(da.stns, da.var, da.days)
+    rows = np.array([0, 2, 10, 7, 249, 240]) + synth.TILE_ROW0
+    cols = np.array([0, 3, 4, 12, 249, 200]) + synth.TILE_COL0
+    lat, lon = synth.grid_lats(rows), synth.grid_lons(cols)
+    elev = f.elev(lon, lat)
+    lst = np.stack([f.lst(1, m, lon, lat, elev) for m in range(1, 13)], axis=1)
+    kn, _, _, st0 = ctx.nngh_params(lat, lon)
+    idx, _, _, _ = ctx.knn(lat, lon, 147)
+    mean, var, st = ctx.krig(lat, lon, elev, lst, mth=0)
+    ia, ib = int(np.flatnonzero(good == a)[0]), int(np.flatnonzero(good == b)[0])
+    ss = o.StationSelect(oda, ctx.mask)
+    kt = o.KrigTair(ss)
+    pt = o.build_empty_pt()
+    nsing = 0
+    for i in range(lat.size):
+        nmax = kn[i].max()
+        sees_pair = ia in idx[i, :nmax] and ib in idx[i, :nmax]
+        assert (st[i] == _lib.ST_SINGULAR) == sees_pair
+        pt[o.LAT], pt[o.LON], pt[o.ELEV] = lat[i], lon[i], elev[i]
+        if sees_pair:
+            nsing += 1
+            raised = 0                                    # (numpy's Cholesky lets some months through on a rounded pivot)
+            for m in range(1, 13):
+                pt[o.lst_name(m)] = lst[i, m - 1]
+                try:
+                    kt.krig(pt, m)
+                except o.OracleError as e:
+                    assert e.value.status == o.ST_SINGULAR
+                    raised += 1
+            assert raised >= 1                            # the point fails in the reference loop (interp_tair.py:396-439)
+        else:
+            assert st[i] == 0
+            for m in (1, 7):
+                pt[o.lst_name(m)] = lst[i, m - 1]
+                om, ov = kt.krig(pt, m)
+                assert abs(om - mean[i, m - 1]) < TOL_C and abs(ov - var[i, m - 1]) <= TOL_VAR_REL * abs(ov)
+    assert 3 <= nsing < lat.size
+
+
 def test_gwr_hat_and_daily_vs_oracle(env):
     lat, lon, elev, tdi, lst, _ = _pts(env, 40, 6)
     ctx, oda = env["ctx"][0], env["oda"][0]

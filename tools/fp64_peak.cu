@@ -113,6 +113,31 @@ __global__ void k_dmma_smem(double* out, int iters, int ntiles) {
     if (sm[threadIdx.x] == 12345.678) out[0] = sm[0];
 }
 
+// DMMA and scalar DFMA in the same instruction stream: do they share one execution pipe?  ND DMMAs + NF DFMAs per
+// iteration, all chains independent.  If the two kinds run on separate pipes the time is max(t_dmma, t_dfma), on a
+// shared pipe it is their sum.
+template <int ND, int NF>
+__global__ void k_mixed(double* out, int iters, double a, double b) {
+    double c0[ND > 0 ? ND : 1], c1[ND > 0 ? ND : 1], acc[NF > 0 ? NF : 1];
+#pragma unroll
+    for (int i = 0; i < ND; ++i) { c0[i] = threadIdx.x * 1e-9; c1[i] = i; }
+#pragma unroll
+    for (int i = 0; i < NF; ++i) acc[i] = threadIdx.x * 1e-9 + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < (ND > NF ? ND : NF); ++i) {
+            if (i < ND) dmma884(c0[i], c1[i], a, b);
+            if (i < NF) acc[i] = fma(acc[i], a, b);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < ND; ++i) s += c0[i] + c1[i];
+#pragma unroll
+    for (int i = 0; i < NF; ++i) s += acc[i];
+    if (s == 12345.678) out[0] = s;
+}
+
 template <typename F>
 float timeit(F f, int reps = 5) {
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -152,6 +177,16 @@ int main() {
         printf("{\"bench\": \"dmma_m16n8k8_ilp4\", \"warps_per_sm\": %d, \"tflops\": %.2f}\n", wp, nthreads / 32 * (iters / 2) * 4 * 2048.0 / ms / 1e9);
         ms = timeit([&] { k_dmma16816<4><<<ctas, threads>>>(out, iters / 4, 1.0000001, 1e-9); });
         printf("{\"bench\": \"dmma_m16n8k16_ilp4\", \"warps_per_sm\": %d, \"tflops\": %.2f}\n", wp, nthreads / 32 * (iters / 4) * 4 * 4096.0 / ms / 1e9);
+    }
+    {   // shared-pipe test at 32 warps per SM: 4 DMMAs (4 x 16 pipe cycles per SMSP) vs 8 DFMAs (8 x 2 cycles) per iteration
+        int threads = 256, ctas = sms * 4;
+        float t_d = timeit([&] { k_mixed<4, 0><<<ctas, threads>>>(out, iters, 1.0000001, 1e-9); });
+        float t_f = timeit([&] { k_mixed<0, 8><<<ctas, threads>>>(out, iters, 1.0000001, 1e-9); });
+        float t_m = timeit([&] { k_mixed<4, 8><<<ctas, threads>>>(out, iters, 1.0000001, 1e-9); });
+        float t_f32 = timeit([&] { k_mixed<0, 32><<<ctas, threads>>>(out, iters, 1.0000001, 1e-9); });
+        float t_m32 = timeit([&] { k_mixed<4, 32><<<ctas, threads>>>(out, iters, 1.0000001, 1e-9); });
+        printf("{\"bench\": \"mixed_dmma4_dfma8\", \"ms_dmma_only\": %.3f, \"ms_dfma_only\": %.3f, \"ms_mixed\": %.3f}\n", t_d, t_f, t_m);
+        printf("{\"bench\": \"mixed_dmma4_dfma32\", \"ms_dmma_only\": %.3f, \"ms_dfma_only\": %.3f, \"ms_mixed\": %.3f}\n", t_d, t_f32, t_m32);
     }
     // smem-fed: 66 tiles (n=87 matrix), per-CTA private, 1..8 warps per CTA, as many CTAs per SM as fit
     CK(cudaFuncSetAttribute(k_dmma_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -50,7 +50,7 @@ namespace twxi {
 #define TWXI_KED_PAIR 1          // workers update two tile rows per pass (four independent DMMA chains)
 #endif
 
-constexpr int KED_HDR = 8 + 32 + 2 * 128;         // doubles: flag + mbarrier, 2^(j/32), -inv(L_KK) x2, N_diag x2
+constexpr int KED_HDR = 8 + 64 + 2 * 128;         // doubles: flag + mbarrier, 2^(j/64), -inv(L_KK) x2, N_diag x2
 constexpr int KED_MAXNB = 32;           // size classes NBv = 1..32 (n <= 255)
 
 struct KedArgs {
@@ -83,13 +83,14 @@ __device__ __forceinline__ int htile(int I, int J) { return I * (I + 1) / 2 + J;
 
 // ---- 1. compact distance tiles -------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) hgather_kernel(StnTable st, int q0, int nq, int k1, const int32_t* idx,
-                                                      const int32_t* nn, const int32_t* status, double* hc,
-                                                      size_t hc_stride) {
+                                                      const int32_t* nn, int32_t* status, double* hc,
+                                                      size_t hc_stride, int single_mth) {
     __shared__ int sidx[256];
     const int q = q0 + blockIdx.x;
     if (status[q] != TWXI_ST_OK) return;
     int nmax = 0;
-    for (int m = 0; m < 12; ++m) nmax = max(nmax, nn[(size_t)q * 24 + m]);
+    for (int m = 0; m < 12; ++m)
+        if (single_mth < 0 || m == single_mth) nmax = max(nmax, nn[(size_t)q * 24 + m]);
     if (nmax < 1) return;
     for (int j = threadIdx.x; j < nmax; j += blockDim.x) sidx[j] = idx[(size_t)q * k1 + j];
     __syncthreads();
@@ -102,83 +103,144 @@ __global__ void __launch_bounds__(256) hgather_kernel(StnTable st, int q0, int n
         for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
             const int i = 8 * I + ((e >> 3) & 7), j = 8 * (e >> 6) + (e & 7);
             double h = 0.0;
-            if (i < nmax && j < nmax && j != i) h = st.H[(size_t)sidx[i] * N + sidx[j]];   // diagonal tiles: both triangles
+            if (i < nmax && j < nmax && j != i) {             // diagonal tiles: both triangles
+                h = st.H[(size_t)sidx[i] * N + sidx[j]];
+                // two neighbours at the same location make V singular (gstat stops with an error, the drivers leave the
+                // fill value): decided here, exactly, instead of by the sign of a rounded pivot; the covariance
+                // evaluation of the solve then needs no h == 0 case
+                if (h == 0.0) atomicCAS(status + q, TWXI_ST_OK, TWXI_ST_SINGULAR);
+            }
             row[e] = h;
         }
     }
 }
 
 // ---- 2. counting sort of the (point, month) problems by size class -------------------------------------------------
-__global__ void ked_bin_kernel(int q0, int nq, int single_mth, const int32_t* nn, const int32_t* status,
-                               int32_t* bcount) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nq * 12) return;
+// STABLE (problems of a class stay in (point, month) order): the months of a point that fall into one class sit next
+// to each other in the list, are handed to neighbouring CTAs and read the point's distance tiles at about the same time,
+// so all but the first read are L2 hits; and the order of the list no longer depends on the timing of atomics.
+constexpr int KED_NCLS = 24;             // classes 0 .. KED_NBMAX (21) fit; one warp per class in the scan
+__device__ __forceinline__ int ked_class_of(int t, int q0, int nq, int single_mth, const int32_t* nn, const int32_t* status,
+                                            int& pid, int& n) {
+    pid = 0; n = 0;
+    if (t >= nq * 12) return KED_NCLS;                        // KED_NCLS: not a problem
     const int q = q0 + t / 12, m = t % 12;
-    if (single_mth >= 0 && m != single_mth) return;
-    if (status[q] != TWXI_ST_OK) return;
-    const int n = nn[(size_t)q * 24 + m];
-    if (n < 1) return;
-    atomicAdd(&bcount[(n + 7) >> 3], 1);
+    if (single_mth >= 0 && m != single_mth) return KED_NCLS;
+    if (status[q] != TWXI_ST_OK) return KED_NCLS;
+    n = nn[(size_t)q * 24 + m];
+    if (n < 1) return KED_NCLS;
+    pid = q * 12 + m;
+    return (n + 7) >> 3;
 }
-__global__ void ked_scan_kernel(const int32_t* bcount, int32_t* bstart, int32_t* fill) {
+// per block of 256 problems: number of problems in each class
+__global__ void __launch_bounds__(256) ked_bin_kernel(int q0, int nq, int single_mth, const int32_t* nn, const int32_t* status,
+                                                      int32_t* blockcnt) {
+    __shared__ int cnt[KED_NCLS + 1];
+    if (threadIdx.x <= KED_NCLS) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    int pid, n;
+    const int b = ked_class_of(blockIdx.x * 256 + threadIdx.x, q0, nq, single_mth, nn, status, pid, n);
+    atomicAdd(&cnt[b], 1);
+    __syncthreads();
+    if (threadIdx.x < KED_NCLS) blockcnt[(size_t)blockIdx.x * KED_NCLS + threadIdx.x] = cnt[threadIdx.x];
+}
+// exclusive scan of the block counts of every class (one warp per class), then of the class totals
+__global__ void __launch_bounds__(KED_NCLS * 32) ked_scan_kernel(int nblocks, int32_t* blockcnt, int32_t* bcount, int32_t* bstart) {
+    __shared__ int total[KED_NCLS];
+    const int b = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int carry = 0;
+    for (int base = 0; base < nblocks; base += 32) {
+        const int i = base + lane;
+        const int v = i < nblocks ? blockcnt[(size_t)i * KED_NCLS + b] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (i < nblocks) blockcnt[(size_t)i * KED_NCLS + b] = carry + incl - v;      // becomes the block's offset in its class
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) total[b] = carry;
+    __syncthreads();
     if (threadIdx.x == 0) {
-        int s = 0;
-        for (int b = 0; b <= KED_MAXNB; ++b) { bstart[b] = s; s += bcount[b]; fill[b] = 0; }
+        int sacc = 0;
+        for (int k = 0; k < KED_NCLS; ++k) { bstart[k] = sacc; bcount[k] = total[k]; sacc += total[k]; }
     }
 }
-__global__ void ked_scatter_kernel(int q0, int nq, int single_mth, const int32_t* nn, const int32_t* status,
-                                   const int32_t* bstart, int32_t* fill, int2* list) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nq * 12) return;
-    const int q = q0 + t / 12, m = t % 12;
-    if (single_mth >= 0 && m != single_mth) return;
-    if (status[q] != TWXI_ST_OK) return;
-    const int n = nn[(size_t)q * 24 + m];
-    if (n < 1) return;
-    const int b = (n + 7) >> 3;
-    list[bstart[b] + atomicAdd(&fill[b], 1)] = make_int2(q * 12 + m, n);
+__global__ void __launch_bounds__(256) ked_scatter_kernel(int q0, int nq, int single_mth, const int32_t* nn, const int32_t* status,
+                                                          const int32_t* bstart, const int32_t* blockoff, int2* list) {
+    __shared__ int wcnt[8][KED_NCLS + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 8 * (KED_NCLS + 1); i += 256) (&wcnt[0][0])[i] = 0;
+    __syncthreads();
+    int pid, n;
+    const int b = ked_class_of(blockIdx.x * 256 + threadIdx.x, q0, nq, single_mth, nn, status, pid, n);
+    const unsigned same = __match_any_sync(0xffffffffu, b);
+    const int rank = __popc(same & ((1u << lane) - 1u));
+    if (rank == 0) wcnt[warp][b] = __popc(same);
+    __syncthreads();
+    if (b == KED_NCLS) return;
+    int off = rank;
+    for (int w2 = 0; w2 < warp; ++w2) off += wcnt[w2][b];
+    list[bstart[b] + blockoff[(size_t)blockIdx.x * KED_NCLS + b] + off] = make_int2(pid, n);
 }
 
 // ---- 3. the solve ------------------------------------------------------------------------------------------------
-// exp(x) for x <= 0 with ~1e-16 relative error: x = (32 e + j) ln2/32 + r, |r| <= ln2/64,
-// exp(x) = 2^e * 2^(j/32) * P6(r).  Branch-free: 12 FP64 ops + one shared-memory table lookup.
-__device__ __forceinline__ double exp_neg(double x, const double* __restrict__ tab32) {
-    x = fmax(x, -700.0);
-    const double SHIFT = 6755399441055744.0;                  // 2^52 + 2^51: rounds to nearest integer
-    double kd = fma(x, 46.16624130844683, SHIFT);             // 32 / ln2
-    const int ki = __double2loint(kd);
-    kd -= SHIFT;
-    double r = fma(kd, -0.02166084938653512, x);              // ln2/32, low 21 bits zero: k*hi exact
-    r = fma(kd, -5.9631716539705866e-12, r);
-    double p = fma(r, 1.0 / 720.0, 1.0 / 120.0);
-    p = fma(r, p, 1.0 / 24.0);
-    p = fma(r, p, 1.0 / 6.0);
-    p = fma(r, p, 0.5);
-    p = fma(r, p, 1.0);
-    p = fma(r, p, 1.0);
-    const double v = p * tab32[ki & 31];
-    return __hiloint2double(__double2hiint(v) + ((ki >> 5) << 20), __double2loint(v));
-}
-
+// Covariances.  psill * exp(-h / range) for h >= 0 with ~1e-16 relative error: with t = -h / range,
+// t = k ln2/64 + r (|r| <= ln2/128), exp(t) = 2^(k >> 6) * 2^((k & 63)/64) * P5(r); psill is folded into the
+// coefficients of P5, the power-of-two table lives in shared memory.  Branch-free: 11 FP64 operations, one table
+// lookup and five integer operations per value (this is a third of all the instructions of the kriging kernel).
+constexpr int KED_TABN = 64;
 struct CovPar {
-    double c00, psill_eff, nir;      // C(0); psill (0 for the pure nugget model); -1/range
+    double c00;                      // C(0) = nugget + partial sill
+    double nir, nk;                  // -1/range and -64/(range ln2); 0 for the pure nugget model
+    double c0, c2, c3, c4, c5;       // psill * {1, 1/2, 1/6, 1/24, 1/120} (0 for the pure nugget model)
 };
-// C(h) of an off-diagonal pair: nug+psill at h == 0 (co-located stations -> singular, as in gstat)
-__device__ __forceinline__ double cov(double h, const CovPar& cp, const double* tab32) {
+__device__ __forceinline__ void covpar_set(CovPar& cp, double nug, double psill, double rng) {
+    cp.c00 = nug + psill;
+    // range == 0: pure nugget model, C(h > 0) = 0 (interp.R:223-227).  -1/range is clamped at -250 / km (a range of
+    // 4 m: every covariance between distinct stations is already zero) so that k stays inside 32 bits.
+    const bool nugget_only = !(rng != 0.0) || !(psill != 0.0);
+    const double nir = nugget_only ? 0.0 : fmax(-1.0 / rng, -250.0);
+    const double ps = nugget_only ? 0.0 : psill;
+    cp.nir = nir;
+    cp.nk = nir * 92.33248261689366;                          // 64 / ln2
+    cp.c0 = ps; cp.c2 = ps * 0.5; cp.c3 = ps * (1.0 / 6.0); cp.c4 = ps * (1.0 / 24.0); cp.c5 = ps * (1.0 / 120.0);
+}
+// C(h) for h > 0 (also the value the exponential model takes at h == 0, without the nugget)
+__device__ __forceinline__ double cov_pos(double h, const CovPar& cp, const double* __restrict__ tab) {
 #if TWXI_KED_FAKE == 2
-    const double e = cp.psill_eff * (h * cp.nir);
+    return cp.c0 * (h * cp.nir);
 #else
-    const double e = cp.psill_eff * exp_neg(h * cp.nir, tab32);
+    const double SHIFT = 6755399441055744.0;                  // 2^52 + 2^51: rounds to nearest integer
+    double kd = fma(h, cp.nk, SHIFT);
+    int ki = __double2loint(kd);
+    kd -= SHIFT;
+    double r = fma(kd, -0.01083042469326756, h * cp.nir);      // ln2/64, low 21 bits zero: k*hi exact
+    r = fma(kd, -2.9815858269852933e-12, r);
+    double p = fma(r, cp.c5, cp.c4);
+    p = fma(r, p, cp.c3);
+    p = fma(r, p, cp.c2);
+    p = fma(r, p, cp.c0);
+    p = fma(r, p, cp.c0);
+    ki = max(ki, -KED_TABN * 1000);                                // below 2^-1000 the value does not matter, the exponent must stay valid
+    const double v = p * tab[ki & (KED_TABN - 1)];
+    return __hiloint2double(__double2hiint(v) + ((ki >> 6) << 20), __double2loint(v));
 #endif
+}
+// C(h) of a pair that may be co-located (point - station): nug+psill at h == 0
+__device__ __forceinline__ double cov(double h, const CovPar& cp, const double* tab) {
+    const double e = cov_pos(h, cp, tab);
     return h == 0.0 ? cp.c00 : e;
 }
 // V tile (I, K) from its distance tile in C-fragment layout; lane holds (i, j) and (i, j+1).
 // `plain` (warp-uniform): the tile is strictly below the diagonal and inside the n x n block, so no masking.
 __device__ __forceinline__ double2 cov_tile(double2 h, int i, int j, int n, const CovPar& cp, const double* tab32,
                                             bool plain) {
-    double2 v;
-    v.x = cov(h.x, cp, tab32);
-    v.y = cov(h.y, cp, tab32);
+    double2 v;                                                // (co-located station pairs never get here: hgather)
+    v.x = cov_pos(h.x, cp, tab32);
+    v.y = cov_pos(h.y, cp, tab32);
     if (!plain) {                                             // diagonal tiles are kept fully symmetric (elim8_mma)
         if (j == i) v.x = cp.c00;
         if (j + 1 == i) v.y = cp.c00;
@@ -347,9 +409,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
     extern __shared__ __align__(16) double sm[];
     int* flag = reinterpret_cast<int*>(sm);                   // [0] singular
     void* mbar = sm + 2;                                      // mbarrier of the distance-tile bulk copies
-    double* tab32 = sm + 8;                                   // 32: 2^(j/32)
-    double2* Wt2 = reinterpret_cast<double2*>(sm + 40);       // 2 x 64: -inv(L_KK), double-buffered by K & 1
-    double2* Nd2 = reinterpret_cast<double2*>(sm + 168);      // 2 x 64: N_diag of column c, double-buffered by c & 1
+    double* tab32 = sm + 8;                                   // 64: 2^(j/64)
+    double2* Wt2 = reinterpret_cast<double2*>(sm + 72);       // 2 x 64: -inv(L_KK), double-buffered by K & 1
+    double2* Nd2 = reinterpret_cast<double2*>(sm + 200);      // 2 x 64: N_diag of column c, double-buffered by c & 1
     double* tiles = sm + KED_HDR;
     constexpr int NT = (NW + 1) * 32;
     constexpr int NJ = (NMAX + NT - 1) / NT;                  // stations per thread in the B' build (n <= NMAX)
@@ -359,7 +421,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
     const int NB = a.nbv;
     const int count = a.bcount[NB], start = a.bstart[NB];
     const int N = a.st.n;
-    if (tid < 32) tab32[tid] = exp2((double)tid / 32.0);
+    for (int i = tid; i < KED_TABN; i += NT) tab32[i] = exp2((double)i / KED_TABN);
     if (tid == 0) mbar_init(mbar, 1);
     uint32_t parity = 0;
 
@@ -432,9 +494,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
             if (NB > 1) hd1 = p.hc2[htile(1, 1) * 32];
         }
         if (warp == NW - 1 && NB > 2) hd = p.hc2[htile(2, 2) * 32];     // look-ahead worker (u == 0)
-        p.cp.c00 = nug + psill;
-        p.cp.psill_eff = rng != 0.0 ? psill : 0.0;            // range == 0: pure nugget model (interp.R:223-227)
-        p.cp.nir = rng != 0.0 ? -1.0 / rng : 0.0;
+        covpar_set(p.cp, nug, psill, rng);
         if (warp == NW && pending) {
             ked_finish(a.mean, a.var, a.status, pend_S, pend_q, pend_m, pend_yref, pend_c00, lane);
             pending = false;
@@ -479,13 +539,13 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
             for (; t + 3 * NWT < T0; t += 4 * NWT) {
                 const double2 h1 = tl2[t * 32], h2 = tl2[(t + NWT) * 32], h3 = tl2[(t + 2 * NWT) * 32], h4 = tl2[(t + 3 * NWT) * 32];
                 double2 v1, v2, v3, v4;
-                v1.x = -cov(h1.x, p.cp, tab32); v2.x = -cov(h2.x, p.cp, tab32); v3.x = -cov(h3.x, p.cp, tab32); v4.x = -cov(h4.x, p.cp, tab32);
-                v1.y = -cov(h1.y, p.cp, tab32); v2.y = -cov(h2.y, p.cp, tab32); v3.y = -cov(h3.y, p.cp, tab32); v4.y = -cov(h4.y, p.cp, tab32);
+                v1.x = -cov_pos(h1.x, p.cp, tab32); v2.x = -cov_pos(h2.x, p.cp, tab32); v3.x = -cov_pos(h3.x, p.cp, tab32); v4.x = -cov_pos(h4.x, p.cp, tab32);
+                v1.y = -cov_pos(h1.y, p.cp, tab32); v2.y = -cov_pos(h2.y, p.cp, tab32); v3.y = -cov_pos(h3.y, p.cp, tab32); v4.y = -cov_pos(h4.y, p.cp, tab32);
                 tl2[t * 32] = v1; tl2[(t + NWT) * 32] = v2; tl2[(t + 2 * NWT) * 32] = v3; tl2[(t + 3 * NWT) * 32] = v4;
             }
             for (; t < T0; t += NWT) {
                 const double2 h1 = tl2[t * 32];
-                tl2[t * 32] = make_double2(-cov(h1.x, p.cp, tab32), -cov(h1.y, p.cp, tab32));
+                tl2[t * 32] = make_double2(-cov_pos(h1.x, p.cp, tab32), -cov_pos(h1.y, p.cp, tab32));
             }
             const bool plain = 8 * NB <= n;                   // last row of V: identity padding beyond n
             for (int c = warp; c < NB - 1; c += NW + 1) {
@@ -578,22 +638,39 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
     if (warp == NW && pending) ked_finish(a.mean, a.var, a.status, pend_S, pend_q, pend_m, pend_yref, pend_c00, lane);
 }
 
-// ---- 3b. one warp per problem (v5) ------------------------------------------------------------------------------------
+// ---- 3b. one warp per problem (v6) ------------------------------------------------------------------------------------
 // The same left-looking tile algorithm executed by ONE warp per problem (one-warp CTAs): no CTA barriers, no work duplicated
-// between warps, and the instruction-level parallelism comes from register blocking (a group of up to KW_R tile rows shares
-// every L(c,J) operand) instead of from warps that wait for each other.  All tile slots are lane-private (C-fragment
-// layout in, C-fragment layout out), so the stage loop needs a __syncwarp only around the transposition of -inv(L_KK).
+// between warps; the instruction-level parallelism comes from register blocking (a group of up to four tile rows shares
+// every L(c,J) operand).  All tile slots are lane-private (C-fragment layout in, C-fragment layout out), so the stage loop
+// needs a __syncwarp only around the transposition of -inv(L_KK).
 // Stage K (pivot tile D_K in registers, column c = K+1):
-//   phase P  N(I,c) += sum_{J<K} L(I,J) L(c,J)'  for the rows I > c, and the same sum for the next pivot tile; none of it
-//            depends on D_K, so the serial pivot chain of D_K (chol8 steps, ~110 cycles each) is dealt out one step per
-//            J iteration and runs in the shadow of the DMMA stream;
+//   phase P  N(I,c) = -C(h(I,c)) + sum_{J<K} L(I,J) L(c,J)'  for the rows I > c, and the same sum for the next pivot tile;
+//            none of it depends on D_K, so the serial pivot chain of D_K (chol8 steps, ~110 cycles each) is dealt out one
+//            step per J iteration and runs in the shadow of the DMMA stream;
 //   phase F  -W = -inv(L_KK)';  L(c,K) = N(c,K)(-W)';  D_{K+1} = -(N_diag + L(c,K)L(c,K)');
 //            rows I > c:  L(I,K) = N(I,K)(-W)', N(I,c) += L(I,K)L(c,K)'.
-// Tile row c is dead after stage K, so the distance tiles of the warp's NEXT problem (same size class, same slots) are
-// fetched into it right away with a TMA bulk copy: the loads of problem i+1 hide behind the stages of problem i with no
-// second buffer.
-constexpr int KW_HDR = 8 + 32 + 64;     // doubles: mbarrier, 2^(j/32), -inv(L_KK) transposition buffer
-constexpr int KW_R = 4;                 // tile rows per register-blocked group
+// Shared memory is what bounds the warps per SM, so tiles live only while they are needed: tile (I,J) is born when
+// column J is first touched (stage J-1) and dies after stage I-1 (row I has been the pivot row).  Along a diagonal
+// d = I-1-J the live tiles are at most d+2 consecutive columns, so every diagonal is a RING of min(d+2, NB-1-d) slots
+// (slot = base[d] + J mod cap[d]); the footprint falls from NB(NB+1)/2 to ~0.6x of it (39 instead of 55 tiles at NB = 10).
+// The raw distance tile of (I,J) is fetched by cp.async straight into its future slot one stage ahead (each lane copies
+// and later reads only its own 16 bytes: no barrier), and is turned into -C(h) in registers when phase P initialises the
+// accumulator, so the exponentials overlap the DMMA stream instead of forming a separate pass.
+constexpr int KW_HDR = 8 + 64 + 64;     // doubles: pad, 2^(j/64), -inv(L_KK) transposition buffer
+
+__host__ __device__ inline int kw_cap(int nb, int d) { return d + 2 < nb - 1 - d ? d + 2 : nb - 1 - d; }
+__host__ __device__ inline int kw_ring_slots(int nb) {          // ring slots of the V rows (the B' row follows them)
+    int s = 0;
+    for (int d = 0; d + 1 < nb; ++d) s += kw_cap(nb, d);
+    return s;
+}
+__host__ __device__ inline int kw_tab_doubles(int nb) { return (((nb + 1) * nb * 2 + 15) / 16) * 2; }
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 struct WChain {
     double2 a, z;
@@ -607,17 +684,18 @@ __device__ __forceinline__ void wchain_init(WChain& c, double2 D, int lane) {
     c.z.y = (2 * q + 1 == r) ? 1.0 : 0.0;
     c.dx = 1.0; c.dy = 1.0; c.rprev = 1.0; c.ok = true;
 }
-// pivot k of chol8_inverse_t (twxi_internal.cuh) with a run-time k
-__device__ __forceinline__ void wchain_step(WChain& c, int k, int lane) {
-    const int r = lane >> 2, q = lane & 3, kq = k >> 1;
-    const bool odd = k & 1;
-    const double mine = odd ? c.a.y : c.a.x;
+// pivot k = 2 kq + ODD of chol8_inverse_t (twxi_internal.cuh) with a run-time kq
+template <bool ODD>
+__device__ __forceinline__ void wchain_step_p(WChain& c, int kq, int lane) {
+    const int r = lane >> 2, q = lane & 3;
+    const int k = 2 * kq + (ODD ? 1 : 0);
+    const double mine = ODD ? c.a.y : c.a.x;
     const double e = (q == kq) ? mine : 0.0;
     const double dk = __shfl_sync(0xffffffffu, mine, 4 * k + kq);
     const double ax = c.a.x * c.rprev, ay = c.a.y * c.rprev;
     c.ok = c.ok && (dk > 0.0);
     const double piv = dk * c.rprev;
-    if (kq == q) { if (odd) c.dy = piv; else c.dx = piv; }
+    if (kq == q) { if (ODD) c.dy = piv; else c.dx = piv; }
     if (k < 7) {
         const double es = -e * c.rprev;
         double2 t = make_double2(dk * ax, dk * ay);
@@ -625,92 +703,177 @@ __device__ __forceinline__ void wchain_step(WChain& c, int k, int lane) {
         c.a = t;
         const double p = fast_rcp(dk);
         const double mneg = (r == k) ? 0.0 : -e * p;
-        dmma(c.z, odd ? c.z.y : c.z.x, mneg);
+        dmma(c.z, ODD ? c.z.y : c.z.x, mneg);
         c.rprev = p;
     }
 }
-
-// phase P for RR rows I0.. (all > c); DIAG: also the pivot tile of column c (accD)
-template <int RR, bool DIAG>
-__device__ __forceinline__ void kw_partial(double2* tl2, int c, int K, int I0, double2& accD, WChain& ch, int& ks, int lane) {
-    const double2* pB = tl2 + ltile(c, 0) * 32;
-    const double2* pA[RR > 0 ? RR : 1];
-    double2 acc[RR > 0 ? RR : 1], av[RR > 0 ? RR : 1];
-#pragma unroll
-    for (int r = 0; r < RR; ++r) {
-        pA[r] = tl2 + ltile(I0 + r, 0) * 32;
-        acc[r] = pA[r][c * 32];
-        av[r] = pA[r][0];
-    }
-    double2 b = pB[0];
-    for (int J = 0; J < K; ++J) {
-        const double2 bc = b;
-        double2 ac[RR > 0 ? RR : 1];
-#pragma unroll
-        for (int r = 0; r < RR; ++r) ac[r] = av[r];
-        b = pB[(J + 1) * 32];                                 // slot (c, K) at the last iteration: valid memory, unused
-#pragma unroll
-        for (int r = 0; r < RR; ++r) av[r] = pA[r][(J + 1) * 32];
-        if (DIAG) dmma(accD, bc.x, bc.x);
-#pragma unroll
-        for (int r = 0; r < RR; ++r) dmma(acc[r], ac[r].x, bc.x);
-        if (DIAG) dmma(accD, bc.y, bc.y);
-#pragma unroll
-        for (int r = 0; r < RR; ++r) dmma(acc[r], ac[r].y, bc.y);
-        if (ks < 8) { wchain_step(ch, ks, lane); ++ks; }
-    }
-#pragma unroll
-    for (int r = 0; r < RR; ++r) tl2[(ltile(I0 + r, 0) + c) * 32] = acc[r];
+__device__ __forceinline__ void wchain_step(WChain& c, int k, int lane) {
+    if (k & 1) wchain_step_p<true>(c, k >> 1, lane);
+    else wchain_step_p<false>(c, k >> 1, lane);
 }
 
-// phase F for RR rows I0.. (all > c)
-template <int RR>
-__device__ __forceinline__ void kw_finish(double2* tl2, int c, int K, int I0, const double2 negW, const double2 lk1) {
-    double2 nv[RR], acc[RR], l[RR];
-    int base[RR];
+struct KW {                       // per-problem view of the warp
+    double2* tl2;                 // lane's fragment pointer into the tile slots: slot s is tl2[s * 32]
+    const uint16_t* tab;          // slot of tile (I, J): tab[I * NB + J]
+    const double* tab32;
+    CovPar cp;
+    int NB, lane;
+    bool dead_row;                // this lane's row of tile row NB-1 is identity padding (8 (NB-1) + r8 >= n)
+};
+// -C(h) of an off-diagonal tile of V row I from its raw distances
+__device__ __forceinline__ double2 kw_negcov(const KW& w, double2 h, int I) {
+    double2 v = make_double2(-cov_pos(h.x, w.cp, w.tab32), -cov_pos(h.y, w.cp, w.tab32));
+    if (I == w.NB - 1 && w.dead_row) v = make_double2(0.0, 0.0);
+    return v;
+}
+// Column `col` of V, rows I >= Ifirst: raw distances -> -C(h) in place (two tiles per pass: four exponentials in
+// flight), one step of the pivot chain per pass.  One compact rolled loop shared by every stage: the hot code of a stage
+// has to stay well inside the 32 KB instruction cache, because the warps of an SM are all at different places in it.
+__device__ __forceinline__ void kw_convert_col(const KW& w, int col, int Ifirst, WChain& ch, int& ks) {
+    double2* tl2 = w.tl2;
+    const int NB = w.NB;
+#pragma unroll 1
+    for (int I = Ifirst; I < NB; I += 2) {
+        const bool two = I + 1 < NB;
+        const int s0 = w.tab[I * NB + col] * 32, s1 = w.tab[(two ? I + 1 : I) * NB + col] * 32;
+        const double2 h0 = tl2[s0], h1 = tl2[s1];
+        const double2 v0 = kw_negcov(w, h0, I), v1 = kw_negcov(w, h1, I + 1);
+        tl2[s0] = v0;
+        if (two) tl2[s1] = v1;
+        if (ks < 8) { wchain_step(ch, ks, w.lane); ++ks; }
+    }
+}
+
+// phase P for the rows I0..I0+3 (those <= NB; all > c); diag: also the pivot tile of column c (accD).  A single body
+// with warp-uniform predicates instead of one instantiation per row count (instruction-cache footprint, see above).
+__device__ __forceinline__ void kw_partial(const KW& w, int c, int K, int I0, bool diag, double2& accD, WChain& ch, int& ks) {
+    double2* tl2 = w.tl2;
+    const int NB = w.NB;
+    const uint16_t* tB = w.tab + c * NB;
+    const uint16_t* tA[4];
+    bool v[4];
+    double2 acc[4], av[4];
+    int sdst[4];
 #pragma unroll
-    for (int r = 0; r < RR; ++r) {
-        base[r] = ltile(I0 + r, 0) * 32;
-        nv[r] = tl2[base[r] + K * 32];
-        acc[r] = tl2[base[r] + c * 32];
+    for (int r = 0; r < 4; ++r) {
+        v[r] = I0 + r <= NB;
+        tA[r] = w.tab + (v[r] ? I0 + r : NB) * NB;
+        sdst[r] = v[r] ? tA[r][c] * 32 : 0;                   // (c == NB has no rows below it: tab[NB][NB] does not exist)
+        acc[r] = tl2[sdst[r]];
+        av[r] = tl2[tA[r][0] * 32];
+    }
+    double2 b = tl2[tB[0] * 32];
+#pragma unroll 1
+    for (int J = 0; J < K; ++J) {
+        const double2 bc = b;
+        double2 ac[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) ac[r] = av[r];
+        b = tl2[tB[J + 1] * 32];                              // tile (c, K) at the last iteration: valid slot, unused
+#pragma unroll
+        for (int r = 0; r < 4; ++r) av[r] = tl2[tA[r][J + 1] * 32];
+        if (diag) dmma(accD, bc.x, bc.x);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) if (v[r]) dmma(acc[r], ac[r].x, bc.x);
+        if (diag) dmma(accD, bc.y, bc.y);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) if (v[r]) dmma(acc[r], ac[r].y, bc.y);
+        if (ks < 8) { wchain_step(ch, ks, w.lane); ++ks; }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) if (v[r]) tl2[sdst[r]] = acc[r];
+}
+
+// phase F for the rows I0..I0+3 (those <= NB; all > c)
+__device__ __forceinline__ void kw_finish(const KW& w, int c, int K, int I0, const double2 negW, const double2 lk1) {
+    double2* tl2 = w.tl2;
+    const int NB = w.NB;
+    double2 nv[4], acc[4], l[4];
+    int sK[4], sc[4];
+    bool v[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        v[r] = I0 + r <= NB;
+        const uint16_t* t = w.tab + (v[r] ? I0 + r : NB) * NB;
+        sK[r] = t[K] * 32; sc[r] = t[c] * 32;
+        nv[r] = tl2[sK[r]];
+        acc[r] = tl2[sc[r]];
         l[r] = make_double2(0.0, 0.0);
     }
 #pragma unroll
-    for (int r = 0; r < RR; ++r) dmma(l[r], nv[r].x, negW.x);
+    for (int r = 0; r < 4; ++r) if (v[r]) dmma(l[r], nv[r].x, negW.x);
 #pragma unroll
-    for (int r = 0; r < RR; ++r) dmma(l[r], nv[r].y, negW.y);
+    for (int r = 0; r < 4; ++r) if (v[r]) dmma(l[r], nv[r].y, negW.y);
 #pragma unroll
-    for (int r = 0; r < RR; ++r) tl2[base[r] + K * 32] = l[r];
+    for (int r = 0; r < 4; ++r) if (v[r]) tl2[sK[r]] = l[r];
 #pragma unroll
-    for (int r = 0; r < RR; ++r) dmma(acc[r], l[r].x, lk1.x);
+    for (int r = 0; r < 4; ++r) if (v[r]) dmma(acc[r], l[r].x, lk1.x);
 #pragma unroll
-    for (int r = 0; r < RR; ++r) dmma(acc[r], l[r].y, lk1.y);
+    for (int r = 0; r < 4; ++r) if (v[r]) dmma(acc[r], l[r].y, lk1.y);
 #pragma unroll
-    for (int r = 0; r < RR; ++r) tl2[base[r] + c * 32] = acc[r];
+    for (int r = 0; r < 4; ++r) if (v[r]) tl2[sc[r]] = acc[r];
+}
+
+// everything of stage K that follows the pivot chain; returns false when the pivot tile is not positive definite
+__device__ __forceinline__ bool kw_stage_tail(const KW& w, double* Wd, WChain& ch, int K, double2 accD, double2& D,
+                                              const double2* hc2) {
+    const int lane = w.lane, r8 = lane >> 2, q4 = lane & 3, NB = w.NB, c = K + 1;
+    double2* tl2 = w.tl2;
+    if (!ch.ok) return false;
+    Wd[16 * q4 + r8] = -ch.z.x * fast_rsqrt(ch.dx);           // lane (c, q) holds Z[c][2q..2q+1] = W[2q..2q+1][c]
+    Wd[16 * q4 + 8 + r8] = -ch.z.y * fast_rsqrt(ch.dy);
+    __syncwarp();
+    const double2 negW = reinterpret_cast<const double2*>(Wd)[lane];
+    __syncwarp();
+    double2 lk1 = make_double2(0.0, 0.0);
+    dmma2(lk1, tl2[w.tab[c * NB + K] * 32], negW);            // L(c,K) = N(c,K) (-W)'
+    double2 nd = accD;
+    dmma2(nd, lk1, lk1);
+    D = make_double2(-nd.x, -nd.y);                           // D_{K+1}; -S after the last stage
+    for (int I0 = c + 1; I0 <= NB; I0 += 4) kw_finish(w, c, K, I0, negW, lk1);     // rows below c (the B' row included)
+    // the slots of column K+2 are free now (their previous occupants belonged to tile row K+1 = c): fetch its distances
+    for (int I = K + 3; I < NB; ++I) cp_async16(tl2 + w.tab[I * NB + K + 2] * 32, hc2 + htile(I, K + 2) * 32);
+    cp_async_commit();
+    return true;
 }
 
 template <int MINB, int NMAX>
 __global__ void __launch_bounds__(32, MINB) ked_warp_kernel(KedArgs a) {
     extern __shared__ __align__(16) double sm[];
-    void* mbar = sm;                                          // mbarrier of the distance-tile bulk copies
-    double* tab32 = sm + 8;                                   // 32: 2^(j/32)
-    double* Wd = sm + 40;                                     // 64: -inv(L_KK), row-major
-    double* tiles = sm + KW_HDR;
+    double* tab32 = sm + 8;                                   // 64: 2^(j/64)
+    double* Wd = sm + 72;                                     // 64: -inv(L_KK), row-major
+    const int NB = a.nbv;
+    uint16_t* tab = reinterpret_cast<uint16_t*>(sm + KW_HDR);
+    double* tiles = sm + KW_HDR + kw_tab_doubles(NB);
     constexpr int NJ = (NMAX + 31) / 32;                      // stations per lane in the B' build (n <= NMAX)
 
     const int lane = threadIdx.x;
-    const int NB = a.nbv;
     const int count = a.bcount[NB], start = a.bstart[NB];
     const int N = a.st.n;
     const int r8 = lane >> 2, q4 = lane & 3;
     int slot = blockIdx.x;
     if (slot >= count) return;
-    tab32[lane] = exp2((double)lane / 32.0);
-    if (lane == 0) mbar_init(mbar, 1);
+    for (int i = lane; i < KED_TABN; i += 32) tab32[i] = exp2((double)i / KED_TABN);
+    const int nring = kw_ring_slots(NB);
+    for (int e = lane; e < (NB + 1) * NB; e += 32) {          // slot table
+        const int I = e / NB, J = e - I * NB;
+        int s = 0;
+        if (I >= 1 && J < I) {
+            if (I == NB) {
+                s = nring + J;
+            } else {
+                const int d = I - 1 - J;
+                for (int dd = 0; dd < d; ++dd) s += kw_cap(NB, dd);
+                s += J % kw_cap(NB, d);
+            }
+        }
+        tab[e] = (uint16_t)s;
+    }
     __syncwarp();
-    uint32_t parity = 0;
-    double2* const tl2 = reinterpret_cast<double2*>(tiles) + lane;
-    const uint32_t tx_bytes = (uint32_t)(NB * (NB - 1) / 2) * 512u;     // tile rows 1..NB-1, I tiles each
+    KW w;
+    w.tl2 = reinterpret_cast<double2*>(tiles) + lane;
+    w.tab = tab; w.tab32 = tab32; w.NB = NB; w.lane = lane;
+    double2* const tl2 = w.tl2;
 
     int2 desc = a.list[start + slot];
     int2 desc_next = slot + (int)gridDim.x < count ? a.list[start + slot + gridDim.x] : make_int2(0, 0);
@@ -721,17 +884,19 @@ __global__ void __launch_bounds__(32, MINB) ked_warp_kernel(KedArgs a) {
 #pragma unroll
         for (int t = 0; t < NJ; ++t) sj[t] = (lane + t * 32 < desc.y) ? ip[lane + t * 32] : 0;
     }
-    if (lane == 0 && tx_bytes) {                              // distance tiles of the first problem
-        const double* hc = a.hc + (size_t)(desc.x / 12 - a.q0) * a.hc_stride;
-        mbar_expect_tx(mbar, tx_bytes);
-        for (int I = 1; I < NB; ++I) bulk_g2s(tiles + ltile(I, 0) * 64, hc + htile(I, 0) * 64, (uint32_t)I * 512u, mbar);
+    {   // distance tiles of columns 0 and 1 of the first problem
+        const double2* h2 = reinterpret_cast<const double2*>(a.hc + (size_t)(desc.x / 12 - a.q0) * a.hc_stride) + lane;
+        for (int I = 1; I < NB; ++I) cp_async16(tl2 + tab[I * NB] * 32, h2 + htile(I, 0) * 32);
+        for (int I = 2; I < NB; ++I) cp_async16(tl2 + tab[I * NB + 1] * 32, h2 + htile(I, 1) * 32);
+        cp_async_commit();
     }
     for (; slot < count; slot += gridDim.x) {
         const int pid = desc.x, n = desc.y;
         const int q = pid / 12, m = pid - q * 12;
         const bool has_next = slot + (int)gridDim.x < count;
         const double2* hc2 = reinterpret_cast<const double2*>(a.hc + (size_t)(q - a.q0) * a.hc_stride) + lane;
-        // ---- gathers of the augmented rows (one station per lane and pass; indices prefetched during the previous problem)
+        // ---- gathers of the augmented rows (one station per lane and pass; indices prefetched during the previous
+        // problem); they are consumed after the first pivot chain
         const double* lstm = a.st.lst + (size_t)m * N;
         const double* normm = a.st.norm + (size_t)m * N;
         const double yref = normm[s_first];
@@ -750,47 +915,22 @@ __global__ void __launch_bounds__(32, MINB) ked_warp_kernel(KedArgs a) {
         const double lon0 = a.qlon[q], lat0 = a.qlat[q], elev0 = a.qelev[q], lst0 = a.qlst[(size_t)q * 12 + m];
         const double2 hd0 = hc2[0];                           // raw distances of the diagonal tiles 0 and 1
         double2 hdn = NB > 1 ? hc2[htile(1, 1) * 32] : make_double2(0.0, 0.0);
-        CovPar cp;
-        cp.c00 = nug + psill;
-        cp.psill_eff = rng != 0.0 ? psill : 0.0;              // range == 0: pure nugget model (interp.R:223-227)
-        cp.nir = rng != 0.0 ? -1.0 / rng : 0.0;
+        covpar_set(w.cp, nug, psill, rng);
+        w.dead_row = 8 * (NB - 1) + r8 >= n;
         // prefetch: descriptor two problems ahead, neighbour indices of the next problem
         desc = desc_next;
         if (slot + 2 * (int)gridDim.x < count) desc_next = a.list[start + slot + 2 * gridDim.x];
-        const double* hc_next = a.hc;
+        const double2* hcn2 = hc2;
         if (has_next) {
             const int32_t* ip = a.idx + (size_t)(desc.x / 12) * a.k1;
-            hc_next = a.hc + (size_t)(desc.x / 12 - a.q0) * a.hc_stride;
+            hcn2 = reinterpret_cast<const double2*>(a.hc + (size_t)(desc.x / 12 - a.q0) * a.hc_stride) + lane;
             s_first = ip[0];
 #pragma unroll
             for (int t = 0; t < NJ; ++t) sj[t] = (lane + t * 32 < desc.y) ? ip[lane + t * 32] : 0;
         }
-        if (tx_bytes) mbar_wait(mbar, parity);                // distance tiles have landed in their slots
-        parity ^= 1u;
-        // ---- covariances in place: slot <- -C(h).  Rows 1..NB-2 need no masking; four tiles per pass
-        {
-            const int T0 = NB >= 2 ? ltile(NB - 1, 0) : 0;
-            int t = 0;
-            for (; t + 3 < T0; t += 4) {
-                const double2 h1 = tl2[t * 32], h2 = tl2[(t + 1) * 32], h3 = tl2[(t + 2) * 32], h4 = tl2[(t + 3) * 32];
-                double2 v1, v2, v3, v4;
-                v1.x = -cov(h1.x, cp, tab32); v2.x = -cov(h2.x, cp, tab32); v3.x = -cov(h3.x, cp, tab32); v4.x = -cov(h4.x, cp, tab32);
-                v1.y = -cov(h1.y, cp, tab32); v2.y = -cov(h2.y, cp, tab32); v3.y = -cov(h3.y, cp, tab32); v4.y = -cov(h4.y, cp, tab32);
-                tl2[t * 32] = v1; tl2[(t + 1) * 32] = v2; tl2[(t + 2) * 32] = v3; tl2[(t + 3) * 32] = v4;
-            }
-            for (; t < T0; ++t) {
-                const double2 h1 = tl2[t * 32];
-                tl2[t * 32] = make_double2(-cov(h1.x, cp, tab32), -cov(h1.y, cp, tab32));
-            }
-            const bool plain = 8 * NB <= n;                   // last row of V: identity padding beyond n
-            for (int c = 0; c < NB - 1; ++c) {
-                const double2 v = cov_tile(tl2[(T0 + c) * 32], 8 * (NB - 1) + r8, 8 * c + 2 * q4, n, cp, tab32, plain);
-                tl2[(T0 + c) * 32] = make_double2(-v.x, -v.y);
-            }
-        }
         // ---- augmented rows -B' = -[1, dlon, dlat, delev, dlst, y - yref, c0]' into tile row NB
         {
-            double* row = tiles + ltile(NB, 0) * 64;
+            double* row = tiles + nring * 64;
 #pragma unroll
             for (int t = 0; t < NJ; ++t) {
                 const int j = lane + t * 32;
@@ -803,96 +943,62 @@ __global__ void __launch_bounds__(32, MINB) ked_warp_kernel(KedArgs a) {
                     col[24] = in ? (elev0 - gl[t][2]) * 1e-3 : 0.0;
                     col[32] = in ? (lst0 - gl[t][3]) * 0.1 : 0.0;
                     col[40] = in ? yref - gl[t][4] : 0.0;
-                    col[48] = in ? -cov(gl[t][5], cp, tab32) : 0.0;
+                    col[48] = in ? -cov(gl[t][5], w.cp, tab32) : 0.0;
                     col[56] = 0.0;
                 }
             }
         }
         __syncwarp();
-        if (lane == 0 && has_next && tx_bytes) mbar_expect_tx(mbar, tx_bytes);   // armed for the next problem's rows
-
-        // ---- stage loop
-        double2 D = cov_tile(hd0, r8, 2 * q4, n, cp, tab32, false);     // V(0,0)
-        bool singular = false;
-        int next_row = 1;                                     // next tile row of the following problem to fetch
-        for (int K = 0; K < NB; ++K) {
+        // ---- stages (one loop body for every stage: the code of a stage is shared by all of them)
+        double2 D = cov_tile(hd0, r8, 2 * q4, n, w.cp, tab32, false);   // V(0,0)
+        bool ok = true;
+        for (int K = 0; ok && K < NB; ++K) {
             const int c = K + 1;
             double2 accD = make_double2(0.0, 0.0);            // -V(c,c); zero for the S tile (c == NB)
             if (c < NB) {
-                const double2 v = cov_tile(hdn, 8 * c + r8, 8 * c + 2 * q4, n, cp, tab32, false);
+                const double2 v = cov_tile(hdn, 8 * c + r8, 8 * c + 2 * q4, n, w.cp, tab32, false);
                 accD = make_double2(-v.x, -v.y);
             }
             if (c + 1 < NB) hdn = hc2[htile(c + 1, c + 1) * 32];
             WChain ch;
             wchain_init(ch, D, lane);
             int ks = 0;
-            const int mrows = NB - c;                         // rows below c (the B' row included)
-            if (K > 0) {
-                int I0 = c + 1, left = mrows;
-                if (left >= 4) { kw_partial<4, true>(tl2, c, K, I0, accD, ch, ks, lane); I0 += 4; left -= 4; }
-                else if (left == 3) { kw_partial<3, true>(tl2, c, K, I0, accD, ch, ks, lane); left = 0; }
-                else if (left == 2) { kw_partial<2, true>(tl2, c, K, I0, accD, ch, ks, lane); left = 0; }
-                else if (left == 1) { kw_partial<1, true>(tl2, c, K, I0, accD, ch, ks, lane); left = 0; }
-                else { kw_partial<0, true>(tl2, c, K, I0, accD, ch, ks, lane); }
-                for (; left >= 4; left -= 4, I0 += 4) kw_partial<4, false>(tl2, c, K, I0, accD, ch, ks, lane);
-                if (left == 3) kw_partial<3, false>(tl2, c, K, I0, accD, ch, ks, lane);
-                else if (left == 2) kw_partial<2, false>(tl2, c, K, I0, accD, ch, ks, lane);
-                else if (left == 1) kw_partial<1, false>(tl2, c, K, I0, accD, ch, ks, lane);
-            }
+            cp_async_wait_all();                              // column c has landed (columns 0 and 1 for K == 0)
+#pragma unroll 1
+            for (int col = K ? c : 0; col <= c; ++col) kw_convert_col(w, col, col + 1, ch, ks);
+            if (K)                                            // the first group also forms the next pivot tile
+#pragma unroll 1
+                for (int I0 = c + 1; I0 == c + 1 || I0 <= NB; I0 += 4) kw_partial(w, c, K, I0, I0 == c + 1, accD, ch, ks);
+#pragma unroll 1
             while (ks < 8) { wchain_step(ch, ks, lane); ++ks; }
-            if (!ch.ok) { singular = true; break; }
-            Wd[16 * q4 + r8] = -ch.z.x * fast_rsqrt(ch.dx);   // lane (c, q) holds Z[c][2q..2q+1] = W[2q..2q+1][c]
-            Wd[16 * q4 + 8 + r8] = -ch.z.y * fast_rsqrt(ch.dy);
-            __syncwarp();
-            const double2 negW = reinterpret_cast<const double2*>(Wd)[lane];
-            __syncwarp();
-            double2 lk1 = make_double2(0.0, 0.0);
-            dmma2(lk1, tl2[(ltile(c, 0) + K) * 32], negW);    // L(c,K) = N(c,K) (-W)'
-            double2 nd = accD;
-            dmma2(nd, lk1, lk1);
-            D = make_double2(-nd.x, -nd.y);                   // D_{K+1}; -S after the last stage
-            {
-                int I0 = c + 1, left = mrows;
-                for (; left >= 4; left -= 4, I0 += 4) kw_finish<4>(tl2, c, K, I0, negW, lk1);
-                if (left == 3) kw_finish<3>(tl2, c, K, I0, negW, lk1);
-                else if (left == 2) kw_finish<2>(tl2, c, K, I0, negW, lk1);
-                else if (left == 1) kw_finish<1>(tl2, c, K, I0, negW, lk1);
-            }
-            if (has_next && c < NB) {                         // tile row c is dead: fetch it for the next problem
-                __syncwarp();
-                if (lane == 0) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    bulk_g2s(tiles + ltile(c, 0) * 64, hc_next + htile(c, 0) * 64, (uint32_t)c * 512u, mbar);
-                }
-                next_row = c + 1;
-            }
+            ok = kw_stage_tail(w, Wd, ch, K, accD, D, hc2);
         }
-        if (has_next && next_row < NB) {                      // singular problem: the remaining rows of the next one
-            __syncwarp();
-            if (lane == 0) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                for (int I = next_row; I < NB; ++I)
-                    bulk_g2s(tiles + ltile(I, 0) * 64, hc_next + htile(I, 0) * 64, (uint32_t)I * 512u, mbar);
-            }
+        cp_async_wait_all();                                  // (a singular problem may leave one group in flight)
+        if (has_next) {                                       // every V row is dead: columns 0 and 1 of the next problem
+            for (int I = 1; I < NB; ++I) cp_async16(tl2 + tab[I * NB] * 32, hcn2 + htile(I, 0) * 32);
+            for (int I = 2; I < NB; ++I) cp_async16(tl2 + tab[I * NB + 1] * 32, hcn2 + htile(I, 1) * 32);
+            cp_async_commit();
         }
-        if (singular) {
+        if (!ok) {
             if (lane == 0) atomicCAS(a.status + q, TWXI_ST_OK, TWXI_ST_SINGULAR);
         } else {
-            ked_finish(a.mean, a.var, a.status, make_double2(-D.x, -D.y), q, m, yref, cp.c00, lane);
+            ked_finish(a.mean, a.var, a.status, make_double2(-D.x, -D.y), q, m, yref, w.cp.c00, lane);
         }
         __syncwarp();                                         // the B' row of the next problem overwrites tile row NB
     }
 }
 
 static size_t ked_smem_for(int nbv) { return (size_t)(KED_HDR + (nbv * (nbv + 1) / 2) * 64) * sizeof(double); }
-static size_t kw_smem_for(int nbv) { return (size_t)(KW_HDR + (nbv * (nbv + 1) / 2) * 64) * sizeof(double); }
+static size_t kw_smem_for(int nbv) { return (size_t)(KW_HDR + kw_tab_doubles(nbv) + (kw_ring_slots(nbv) + nbv) * 64) * sizeof(double); }
 
 struct KedWork {                 // device scratch of the kriging stage, owned per thread
     double* hc = nullptr;
     size_t hc_bytes = 0;
     int2* list = nullptr;
     size_t list_cap = 0;
-    int32_t* bins = nullptr;     // bcount | bstart | fill, each KED_MAXNB+1
+    int32_t* bins = nullptr;     // bcount | bstart, each KED_MAXNB+1
+    int32_t* blockcnt = nullptr; // per block of 256 problems and class: count, then offset
+    size_t blockcnt_cap = 0;
     int sms = 0;
     int occ[16][KED_MAXNB + 1];   // resident CTAs per SM for (variant, size class)
     int var_for[KED_MAXNB + 1];  // variant chosen for each size class
@@ -919,6 +1025,7 @@ static const KedVariant KED_VARIANTS[] = {
 constexpr int KED_NVARIANTS = sizeof(KED_VARIANTS) / sizeof(KED_VARIANTS[0]);
 static thread_local KedWork g_ked;
 constexpr int KED_NBMAX = 21;
+static_assert(KED_NBMAX < KED_NCLS && KED_NCLS * 32 <= 1024, "size classes must fit the scan kernel");
 
 #ifdef TWXI_KED_PROFILE
 extern "C" int twxi_ked_prof(unsigned long long* out16, int reset) {
@@ -949,6 +1056,7 @@ int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
                 int o = 0;
                 TWXI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, KED_VARIANTS[v].fn, (KED_VARIANTS[v].nw + 1) * 32,
                                                                         KED_VARIANTS[v].nw ? ked_smem_for(nb) : kw_smem_for(nb)));
+                if (const char* e = getenv("TWXI_KW_MAXOCC")) if (!KED_VARIANTS[v].nw) o = std::min(o, atoi(e));   // experiments
                 w.occ[v][nb] = std::max(1, o);
             }
             int v = sel[nb - 1] - '0';
@@ -978,7 +1086,14 @@ int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
         TWXI_CUDA(cudaMalloc((void**)&w.list, (size_t)qcap * 12 * sizeof(int2)));
         w.list_cap = (size_t)qcap * 12;
     }
-    int32_t *bcount = w.bins, *bstart = w.bins + (KED_MAXNB + 1), *fill = w.bins + 2 * (KED_MAXNB + 1);
+    const size_t nblk_cap = ((size_t)qcap * 12 + 255) / 256;
+    if (nblk_cap > w.blockcnt_cap) {
+        if (w.blockcnt) cudaFree(w.blockcnt);
+        w.blockcnt = nullptr; w.blockcnt_cap = 0;
+        TWXI_CUDA(cudaMalloc((void**)&w.blockcnt, nblk_cap * KED_NCLS * sizeof(int32_t)));
+        w.blockcnt_cap = nblk_cap;
+    }
+    int32_t *bcount = w.bins, *bstart = w.bins + (KED_MAXNB + 1);
     KedArgs a;
     a.st = c.st; a.npts = b.npts; a.k1 = b.k1;
     a.idx = b.idx; a.h0 = b.h0; a.nn = b.nn;
@@ -991,15 +1106,14 @@ int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
     for (int q0 = 0; q0 < b.npts; q0 += qcap) {
         const int nq = std::min(qcap, b.npts - q0);
         a.q0 = q0;
-        hgather_kernel<<<nq, 256, 0, c.stream>>>(c.st, q0, nq, b.k1, b.idx, b.nn, b.status, w.hc, hc_stride);
+        hgather_kernel<<<nq, 256, 0, c.stream>>>(c.st, q0, nq, b.k1, b.idx, b.nn, b.status, w.hc, hc_stride, mth >= 1 ? mth - 1 : -1);
         TWXI_LAUNCH_CHECK();
-        TWXI_CUDA(cudaMemsetAsync(bcount, 0, (KED_MAXNB + 1) * sizeof(int32_t), c.stream));
-        const int nt = nq * 12;
-        ked_bin_kernel<<<(nt + 255) / 256, 256, 0, c.stream>>>(q0, nq, single, b.nn, b.status, bcount);
+        const int nt = nq * 12, nblk = (nt + 255) / 256;
+        ked_bin_kernel<<<nblk, 256, 0, c.stream>>>(q0, nq, single, b.nn, b.status, w.blockcnt);
         TWXI_LAUNCH_CHECK();
-        ked_scan_kernel<<<1, 32, 0, c.stream>>>(bcount, bstart, fill);
+        ked_scan_kernel<<<1, KED_NCLS * 32, 0, c.stream>>>(nblk, w.blockcnt, bcount, bstart);
         TWXI_LAUNCH_CHECK();
-        ked_scatter_kernel<<<(nt + 255) / 256, 256, 0, c.stream>>>(q0, nq, single, b.nn, b.status, bstart, fill, w.list);
+        ked_scatter_kernel<<<nblk, 256, 0, c.stream>>>(q0, nq, single, b.nn, b.status, bstart, w.blockcnt, w.list);
         TWXI_LAUNCH_CHECK();
         // largest classes first: they are the long poles
         for (int nbv = nbmax; nbv >= 1; --nbv) {

@@ -1,9 +1,9 @@
 #!/bin/bash
 # per-size-class duration of ked_kernel under each launch variant (ncu launch list, one variable pass each)
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -2
+true
 for cfg in 000000000000000000000 111111111111111111111 222222222222222222222 333333333333333333333 444444444444444444444; do
-  TWXI_KED_VAR=$cfg timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:ked_kernel -c 19 --csv --log-file gpurun_out/kedvar_$cfg.csv python tools/prof_chunk.py 250 250 1 > /dev/null 2>&1
+  TWXI_KED_VAR=$cfg timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:ked_kernel -c 21 --csv --log-file gpurun_out/kedvar_$cfg.csv python tools/prof_chunk.py 250 250 1 > /dev/null 2>&1
 done
 python - <<'PY'
 import csv,glob

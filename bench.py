@@ -289,7 +289,7 @@ def main():
                 "algorithmic_flops_per_step": flops,
                 "launches_per_step": "2 variable passes x one launch per size class NB = ceil(n/8)",
                 "traffic_note": "DRAM bytes (read+write) of all ked_kernel launches of one step, from the committed ncu "
-                                "capture profiles/ked_traffic_r01.json",
+                                "capture profiles/ked_traffic_r01_k.json",
                 "ms_per_step_kernel": krig_ms,
                 "stage_ms": dict(zip(["knn", "nngh_params", "krig", "gwr_daily", "fixer_quantise"],
                                      [round(float(x), 3) for x in stage_ms])),
@@ -316,7 +316,7 @@ def main():
 
 def _ked_traffic():
     try:
-        with open(os.path.join(ROOT, "profiles", "ked_traffic_r01.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "ked_traffic_r01_k.json")) as f:
             d = json.load(f)
         return d["dram_bytes_read"] + d["dram_bytes_write"]
     except Exception:

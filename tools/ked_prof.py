@@ -18,7 +18,8 @@ lib.twxi_ked_prof(buf, 1)
 v = np.array(list(buf), dtype=np.float64)
 n = max(v[0], 1)
 print("problems", int(v[0]))
-for i, nm in ((1, "prologue total"), (2, "  B' build + TMA issue"), (3, "  covariance pass"), (4, "diag: stage loop total"),
+for i, nm in ((1, "prologue total"), (2, "  B' build + TMA issue"), (3, "  covariance pass"), (13, "  wait for the distance tiles (mbarrier)"),
+              (14, "  barrier: previous problem consumed"), (15, "  barrier: prologue done"), (4, "diag: stage loop total"),
               (5, "  barrier wait"), (6, "  chol8_inverse"), (7, "  post-barrier DMMA part")):
     print("   %-28s %9.0f cycles" % (nm, v[i] / n))
 n = max(v[8], 1)

@@ -560,7 +560,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
         const long long tp4 = KCLK();
         __syncthreads();
         const long long tp5 = KCLK();
-        if (warp == NW) { KPROF(0, 1); KPROF(1, tp5 - tp0); KPROF(2, tp2 - tp1); KPROF(3, tp4 - tp3); }
+        if (warp == NW) { KPROF(0, 1); KPROF(1, tp5 - tp0); KPROF(2, tp2 - tp1); KPROF(3, tp4 - tp3); KPROF(13, tp3 - tp2); KPROF(14, tp1 - tp0); KPROF(15, tp5 - tp4); }
         if (warp == 0) KPROF(8, 1);
         long long t_bar = 0, t_x = 0, t_y = 0;
         (void)tp1; (void)tp2; (void)tp3; (void)tp4; (void)t_x; (void)t_y;

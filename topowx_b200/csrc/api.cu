@@ -254,11 +254,45 @@ int twxi_ctx_create(twxi_ctx** out, int device, int n, const double* lon, const 
     if (rc == TWXI_OK) rc = dev_alloc(c->owned, &coslat, n);
     if (rc == TWXI_OK) rc = dev_alloc(c->owned, &H, (size_t)n * n);
     if (rc == TWXI_OK) rc = launch_station_trig(c->stream, n, st.lon, st.lat, lonrad, latrad, coslat);
-    if (rc == TWXI_OK) rc = launch_build_dist_table(c->stream, n, st.lon, st.lat, H);
+    // station-station distance table in Morton order of (lon, lat): H[hpos[a]][hpos[b]] = gcdist(a, b), same bits as the
+    // DB-ordered table (each entry is computed from the same two stations in the same argument order)
+    std::vector<int32_t> hpos(n), order(n);
+    std::vector<double> plon(n), plat(n);
+    {
+        double lo0 = lon[0], lo1 = lon[0], la0 = lat[0], la1 = lat[0];
+        for (int i = 1; i < n; ++i) {
+            lo0 = std::min(lo0, lon[i]); lo1 = std::max(lo1, lon[i]);
+            la0 = std::min(la0, lat[i]); la1 = std::max(la1, lat[i]);
+        }
+        const double sx = lo1 > lo0 ? 65535.0 / (lo1 - lo0) : 0.0, sy = la1 > la0 ? 65535.0 / (la1 - la0) : 0.0;
+        auto spread = [](uint32_t v) {
+            v &= 0xffffu;
+            v = (v | (v << 8)) & 0x00ff00ffu; v = (v | (v << 4)) & 0x0f0f0f0fu;
+            v = (v | (v << 2)) & 0x33333333u; v = (v | (v << 1)) & 0x55555555u;
+            return v;
+        };
+        std::vector<uint32_t> key(n);
+        for (int i = 0; i < n; ++i) {
+            const double fx = (lon[i] - lo0) * sx, fy = (lat[i] - la0) * sy;
+            const uint32_t ix = std::isfinite(fx) ? (uint32_t)fx : 0u, iy = std::isfinite(fy) ? (uint32_t)fy : 0u;
+            key[i] = spread(ix) | (spread(iy) << 1);
+            order[i] = i;
+        }
+        std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return key[x] < key[y]; });
+        for (int p = 0; p < n; ++p) { hpos[order[p]] = p; plon[p] = lon[order[p]]; plat[p] = lat[order[p]]; }
+    }
+    const double *d_plon = nullptr, *d_plat = nullptr;
+    std::vector<void*> tmp;
+    if (rc == TWXI_OK) rc = dev_upload(*c, tmp, &d_plon, plon.data(), (size_t)n);
+    if (rc == TWXI_OK) rc = dev_upload(*c, tmp, &d_plat, plat.data(), (size_t)n);
+    if (rc == TWXI_OK) rc = dev_upload(*c, c->owned, &st.hpos, hpos.data(), (size_t)n);
+    if (rc == TWXI_OK) rc = launch_build_dist_table(c->stream, n, d_plon, d_plat, H);
     if (rc == TWXI_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) {
         set_error("context build failed");
         rc = TWXI_ERR_CUDA;
     }
+    cudaStreamSynchronize(c->stream);
+    for (void* t : tmp) cudaFree(t);
     if (rc != TWXI_OK) {
         twxi_ctx_destroy(c);
         return rc;

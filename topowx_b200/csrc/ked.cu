@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) hgather_kernel(StnTable st, int q0, int n
     for (int m = 0; m < 12; ++m)
         if (single_mth < 0 || m == single_mth) nmax = max(nmax, nn[(size_t)q * 24 + m]);
     if (nmax < 1) return;
-    for (int j = threadIdx.x; j < nmax; j += blockDim.x) sidx[j] = idx[(size_t)q * k1 + j];
+    for (int j = threadIdx.x; j < nmax; j += blockDim.x) sidx[j] = st.hpos[idx[(size_t)q * k1 + j]];
     __syncthreads();
     const int NB = (nmax + 7) >> 3;
     const int N = st.n;

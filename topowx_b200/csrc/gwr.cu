@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(GWR_THREADS, 4) gwr_kernel(GwrArgs a) {
 
     // ---- u = (X'WX)^-1 e_0 from the transposed inverse Cholesky factor Z: (X'WX)^-1 = Z Z' ------------------
     double2 z;
-    bool ok = chol8_inverse_t(A, z, lane);
+    bool ok = chol8_inverse_t<false>(A, z, lane);
     const double r0x = __shfl_sync(0xffffffffu, z.x, kk), r0y = __shfl_sync(0xffffffffu, z.y, kk);   // row 0 of Z
     double part = fma(z.x, r0x, z.y * r0y);
     part += __shfl_xor_sync(0xffffffffu, part, 1);

@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(256) ked_scatter_kernel(int q0, int nq, int si
 // ---- 3. the solve ------------------------------------------------------------------------------------------------
 // Covariances.  psill * exp(-h / range) for h >= 0 with ~1e-16 relative error: with t = -h / range,
 // t = k ln2/64 + r (|r| <= ln2/128), exp(t) = 2^(k >> 6) * 2^((k & 63)/64) * P5(r); psill is folded into the
-// coefficients of P5, the power-of-two table lives in shared memory.  Branch-free: 11 FP64 operations, one table
+// coefficients of P5, the power-of-two table lives in shared memory.  Branch-free: 10 FP64 operations, one table
 // lookup and five integer operations per value (this is a third of all the instructions of the kriging kernel).
 constexpr int KED_TABN = 64;
 struct CovPar {
@@ -217,8 +217,8 @@ __device__ __forceinline__ double cov_pos(double h, const CovPar& cp, const doub
     double kd = fma(h, cp.nk, SHIFT);
     int ki = __double2loint(kd);
     kd -= SHIFT;
-    double r = fma(kd, -0.01083042469326756, h * cp.nir);      // ln2/64, low 21 bits zero: k*hi exact
-    r = fma(kd, -2.9815858269852933e-12, r);
+    const double r = fma(kd, -0.010830424696249145, h * cp.nir);    // ln2/64; the product is exact inside the fma, and the
+                                                              // rounding of the constant costs |k| * 1.2e-18 (< 1e-15 for h < 12 ranges)
     double p = fma(r, cp.c5, cp.c4);
     p = fma(r, p, cp.c3);
     p = fma(r, p, cp.c2);
@@ -692,18 +692,21 @@ __device__ __forceinline__ void wchain_step_p(WChain& c, int kq, int lane) {
     const double mine = ODD ? c.a.y : c.a.x;
     const double e = (q == kq) ? mine : 0.0;
     const double dk = __shfl_sync(0xffffffffu, mine, 4 * k + kq);
-    const double ax = c.a.x * c.rprev, ay = c.a.y * c.rprev;
     c.ok = c.ok && (dk > 0.0);
     const double piv = dk * c.rprev;
     if (kq == q) { if (ODD) c.dy = piv; else c.dx = piv; }
     if (k < 7) {
         const double es = -e * c.rprev;
-        double2 t = make_double2(dk * ax, dk * ay);
+        double2 t = make_double2(piv * c.a.x, piv * c.a.y);
         dmma(t, es, e);
         c.a = t;
         const double p = fast_rcp(dk);
         const double mneg = (r == k) ? 0.0 : -e * p;
-        dmma(c.z, ODD ? c.z.y : c.z.x, mneg);
+        const double zk = __shfl_sync(0xffffffffu, ODD ? c.z.y : c.z.x, (lane & ~3) | kq);
+        const double m0 = __shfl_sync(0xffffffffu, mneg, 8 * q + kq);
+        const double m1 = __shfl_sync(0xffffffffu, mneg, 8 * q + 4 + kq);
+        c.z.x = fma(zk, m0, c.z.x);
+        c.z.y = fma(zk, m1, c.z.y);
         c.rprev = p;
     }
 }

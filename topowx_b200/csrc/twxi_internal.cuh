@@ -238,10 +238,10 @@ __device__ __forceinline__ bool elim8_mma(double2& a, int lane) {
         const double mine = (k & 1) ? a.y : a.x;
         const double e = (q == kq) ? mine : 0.0;              // M[r][k] in the lanes that own column k
         const double dk = __shfl_sync(0xffffffffu, mine, 4 * k + kq);
-        const double ax = a.x * rprev, ay = a.y * rprev;      // in the shadow of the shuffle
         ok = ok && (dk > 0.0);
         const double es = -e * rprev;
-        double2 c = make_double2(dk * ax, dk * ay);           // M <- (d_k M - M[:,k] M[:,k]') / previous pivot
+        const double piv = dk * rprev;                        // (the kernels are bound by FP64-pipe work, not by this chain)
+        double2 c = make_double2(piv * a.x, piv * a.y);       // M <- (d_k M - M[:,k] M[:,k]') / previous pivot
         dmma(c, es, e);
         a = c;
         rprev = fast_rcp(dk);
@@ -252,6 +252,7 @@ __device__ __forceinline__ bool elim8_mma(double2& a, int lane) {
 
 // Returns Z = transpose of inv(chol(A)) in C-fragment layout (A = the SPD tile `a`).  The seven Z updates depend on
 // each other only through Z, so the scheduler is free to run them behind the pivot chain.
+template <bool Z_BY_FMA = true>
 __device__ __forceinline__ bool chol8_inverse_t(double2 a, double2& z, int lane) {
     const int r = lane >> 2, q = lane & 3;
     z.x = (2 * q == r) ? 1.0 : 0.0;
@@ -265,18 +266,28 @@ __device__ __forceinline__ bool chol8_inverse_t(double2 a, double2& z, int lane)
         const double mine = (k & 1) ? a.y : a.x;
         const double e = (q == kq) ? mine : 0.0;              // M[r][k] in the lanes that own column k
         const double dk = __shfl_sync(0xffffffffu, mine, 4 * k + kq);
-        const double ax = a.x * rprev, ay = a.y * rprev;      // in the shadow of the shuffle
         ok = ok && (dk > 0.0);
         const double piv = dk * rprev;
         if (kq == q) { if (k & 1) dy = piv; else dx = piv; }
         if (k < 7) {
             const double es = -e * rprev;
-            double2 c = make_double2(dk * ax, dk * ay);       // M <- (d_k M - M[:,k] M[:,k]') / previous pivot
+            double2 c = make_double2(piv * a.x, piv * a.y);   // M <- (d_k M - M[:,k] M[:,k]') / previous pivot
             dmma(c, es, e);
             a = c;
             const double p = fast_rcp(dk);
             const double mneg = (r == k) ? 0.0 : -e * p;      // Z[c][r] -= Z[c][k] m_rk
-            dmma(z, (k & 1) ? z.y : z.x, mneg);
+            // rank-1 update of Z with plain FMAs: three shuffles and 2 DFMAs (4 FP64-pipe cycles) instead of one DMMA
+            // (16 cycles, three quarters of it multiplying zeros) - DMMA and DFMA share the pipe that bounds the kernels
+            // (the GWR kernel is bound by latency and the shuffle unit instead and keeps the DMMA form)
+            if (Z_BY_FMA) {
+                const double zk = __shfl_sync(0xffffffffu, (k & 1) ? z.y : z.x, (lane & ~3) | kq);
+                const double m0 = __shfl_sync(0xffffffffu, mneg, 8 * q + kq);
+                const double m1 = __shfl_sync(0xffffffffu, mneg, 8 * q + 4 + kq);
+                z.x = fma(zk, m0, z.x);
+                z.y = fma(zk, m1, z.y);
+            } else {
+                dmma(z, (k & 1) ? z.y : z.x, mneg);
+            }
             rprev = p;
         }
     }

@@ -138,6 +138,32 @@ __global__ void k_mixed(double* out, int iters, double a, double b) {
     if (s == 12345.678) out[0] = s;
 }
 
+// DMMA next to FP32 / integer work: does a DMMA hold the issue port of its SM sub-partition while it occupies the FP64
+// pipe?  ND DMMAs + NF FFMAs (+ NF IMADs) per iteration, all chains independent.
+template <int ND, int NF>
+__global__ void k_mixed32(double* out, int iters, double a, double b, float fa, float fb, int ia) {
+    double c0[ND > 0 ? ND : 1], c1[ND > 0 ? ND : 1];
+    float acc[NF > 0 ? NF : 1];
+    int iacc[NF > 0 ? NF : 1];
+#pragma unroll
+    for (int i = 0; i < ND; ++i) { c0[i] = threadIdx.x * 1e-9; c1[i] = i; }
+#pragma unroll
+    for (int i = 0; i < NF; ++i) { acc[i] = threadIdx.x * 1e-3f + i; iacc[i] = threadIdx.x + i; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < (ND > NF ? ND : NF); ++i) {
+            if (i < ND) dmma884(c0[i], c1[i], a, b);
+            if (i < NF) { acc[i] = fmaf(acc[i], fa, fb); iacc[i] = iacc[i] * ia + 7; }
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < ND; ++i) s += c0[i] + c1[i];
+#pragma unroll
+    for (int i = 0; i < NF; ++i) s += acc[i] + iacc[i];
+    if (s == 12345.678) out[0] = s;
+}
+
 template <typename F>
 float timeit(F f, int reps = 5) {
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -187,6 +213,13 @@ int main() {
         float t_m32 = timeit([&] { k_mixed<4, 32><<<ctas, threads>>>(out, iters, 1.0000001, 1e-9); });
         printf("{\"bench\": \"mixed_dmma4_dfma8\", \"ms_dmma_only\": %.3f, \"ms_dfma_only\": %.3f, \"ms_mixed\": %.3f}\n", t_d, t_f, t_m);
         printf("{\"bench\": \"mixed_dmma4_dfma32\", \"ms_dmma_only\": %.3f, \"ms_dfma_only\": %.3f, \"ms_mixed\": %.3f}\n", t_d, t_f32, t_m32);
+    }
+    {   // issue-port test at 32 warps per SM: 4 DMMAs vs 32 FFMA + 32 IMAD per iteration
+        int threads = 256, ctas = sms * 4;
+        float t_d = timeit([&] { k_mixed32<4, 0><<<ctas, threads>>>(out, iters, 1.0000001, 1e-9, 1.0001f, 1e-3f, 3); });
+        float t_f = timeit([&] { k_mixed32<0, 32><<<ctas, threads>>>(out, iters, 1.0000001, 1e-9, 1.0001f, 1e-3f, 3); });
+        float t_m = timeit([&] { k_mixed32<4, 32><<<ctas, threads>>>(out, iters, 1.0000001, 1e-9, 1.0001f, 1e-3f, 3); });
+        printf("{\"bench\": \"mixed_dmma4_ffma32_imad32\", \"ms_dmma_only\": %.3f, \"ms_alu_only\": %.3f, \"ms_mixed\": %.3f}\n", t_d, t_f, t_m);
     }
     // smem-fed: 66 tiles (n=87 matrix), per-CTA private, 1..8 warps per CTA, as many CTAs per SM as fit
     CK(cudaFuncSetAttribute(k_dmma_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -223,6 +223,12 @@ int twxi_interp_chunk(twxi_ctx* ctx_tmin, twxi_ctx* ctx_tmax, const double* wrk_
 int64_t twxi_launch_count(int reset);
 int twxi_set_stage_timing(int enable);
 int twxi_get_stage_ms(float* ms5);
+/*
+ * Device time (ms, CUDA events on the context's stream) of the ked_kernel launches alone - the kriging stage without
+ * the distance-tile gather and the problem sort - summed since the last call, while stage timing is enabled.
+ * bench.py divides the algorithmic FLOPs of the kriging systems by this figure for its roofline object.
+ */
+int twxi_get_ked_kernel_ms(float* ms);
 
 /*
  * Measured FP64 peak of `device` in TFLOP/s: tensor-core DMMA (mma.sync.m8n8k4.f64) and scalar DFMA loops.

@@ -50,6 +50,7 @@ def _load():
         "twxi_launch_count": (i64, [i32]),
         "twxi_set_stage_timing": (i32, [i32]),
         "twxi_get_stage_ms": (i32, [vp]),
+        "twxi_get_ked_kernel_ms": (i32, [vp]),
         "twxi_ctx_create": (i32, [C.POINTER(vp), i32, i32] + [vp] * 11),
         "twxi_ctx_set_obs": (i32, [vp, vp, i32, vp, vp]),
         "twxi_ctx_set_climdivs": (i32, [vp, vp, i32]),

@@ -11,6 +11,7 @@ static thread_local std::string g_error;
 thread_local long long g_launches = 0;
 static thread_local int g_timing = 0;
 static thread_local float g_stage_ms[5] = {0, 0, 0, 0, 0};
+bool stage_timing_on() { return g_timing != 0; }
 
 void set_error(const std::string& s) { g_error = s; }
 

@@ -1027,6 +1027,7 @@ static const KedVariant KED_VARIANTS[] = {
 };
 constexpr int KED_NVARIANTS = sizeof(KED_VARIANTS) / sizeof(KED_VARIANTS[0]);
 static thread_local KedWork g_ked;
+static thread_local std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_ked_events;   // ked_kernel launches, stage timing on
 constexpr int KED_NBMAX = 21;
 static_assert(KED_NBMAX < KED_NCLS && KED_NCLS * 32 <= 1024, "size classes must fit the scan kernel");
 
@@ -1038,6 +1039,22 @@ extern "C" int twxi_ked_prof(unsigned long long* out16, int reset) {
     return 0;
 }
 #endif
+
+extern "C" int twxi_get_ked_kernel_ms(float* ms) {
+    if (!ms) return TWXI_ERR_ARG;
+    float tot = 0.f;
+    for (auto& e : g_ked_events) {
+        float t = 0.f;
+        cudaEventSynchronize(e.second);
+        cudaEventElapsedTime(&t, e.first, e.second);
+        tot += t;
+        cudaEventDestroy(e.first);
+        cudaEventDestroy(e.second);
+    }
+    g_ked_events.clear();
+    *ms = tot;
+    return TWXI_OK;
+}
 
 int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
     if (b.npts <= 0) return TWXI_OK;
@@ -1118,6 +1135,13 @@ int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
         TWXI_LAUNCH_CHECK();
         ked_scatter_kernel<<<nblk, 256, 0, c.stream>>>(q0, nq, single, b.nn, b.status, bstart, w.blockcnt, w.list);
         TWXI_LAUNCH_CHECK();
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        const bool timed = stage_timing_on();
+        if (timed) {
+            TWXI_CUDA(cudaEventCreate(&ev0));
+            TWXI_CUDA(cudaEventCreate(&ev1));
+            TWXI_CUDA(cudaEventRecord(ev0, c.stream));
+        }
         // largest classes first: they are the long poles
         for (int nbv = nbmax; nbv >= 1; --nbv) {
             a.nbv = nbv;
@@ -1126,6 +1150,10 @@ int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
             const int grid = std::min(w.sms * w.occ[v][nbv], std::max(1, nt));
             KED_VARIANTS[v].fn<<<grid, (KED_VARIANTS[v].nw + 1) * 32, smem, c.stream>>>(a);
             TWXI_LAUNCH_CHECK();
+        }
+        if (timed) {
+            TWXI_CUDA(cudaEventRecord(ev1, c.stream));
+            g_ked_events.push_back(std::make_pair(ev0, ev1));
         }
     }
     return TWXI_OK;

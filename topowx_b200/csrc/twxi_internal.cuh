@@ -17,6 +17,7 @@ namespace twxi {
 
 void set_error(const std::string& s);
 extern thread_local long long g_launches;
+bool stage_timing_on();          // twxi_set_stage_timing(1): the kriging launcher brackets its ked_kernel launches with events
 
 #define TWXI_CUDA(expr)                                                                         \
     do {                                                                                        \

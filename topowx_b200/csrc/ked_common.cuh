@@ -1,0 +1,161 @@
+// Pieces shared by the kriging kernels (ked.cu: CTA per problem, the default; ked_warp.cu: one warp per problem).
+#pragma once
+#include "twxi_internal.cuh"
+
+namespace twxi {
+
+#ifndef TWXI_KED_FAKE
+#define TWXI_KED_FAKE 0          // timing experiments only (results are wrong when non-zero)
+#endif
+#ifndef TWXI_KED_PAIR
+#define TWXI_KED_PAIR 1          // workers update two tile rows per pass (four independent DMMA chains)
+#endif
+
+constexpr int KED_MAXNB = 32;           // size classes NBv = 1..32 (n <= 255)
+
+struct KedArgs {
+    StnTable st;
+    int npts, k1, q0;
+    const int32_t* idx;
+    const double* h0;
+    const int32_t* nn;
+    const double* vario;       // [npts][12][3], or [npts][3] when vario_is_override
+    int vario_is_override;
+    const double* qlon;
+    const double* qlat;
+    const double* qelev;
+    const double* qlst;        // [npts][12]
+    const double* hc;          // compact distance tiles of points q0.. (stride hc_stride doubles per point)
+    size_t hc_stride;
+    const int2* list;          // (problem id q*12 + m, n) sorted by size class
+    const int32_t* bstart;     // [KED_MAXNB+1]
+    const int32_t* bcount;
+    int nbv;                   // size class of this launch
+    double* mean;              // [npts][12]
+    double* var;
+    int32_t* status;
+};
+
+// shared-memory L tiles: rows 1..NBv, row I holds tiles J = 0..I-1 (diagonal tiles are never stored)
+__device__ __forceinline__ int ltile(int I, int J) { return I * (I - 1) / 2 + J; }
+// compact distance tiles: rows 0..NB-1, row I holds tiles J = 0..I
+__device__ __forceinline__ int htile(int I, int J) { return I * (I + 1) / 2 + J; }
+
+
+// ---- covariances, barrier / bulk-copy helpers, the 5x5 GLS --------------------------------------------------------
+// Covariances.  psill * exp(-h / range) for h >= 0 with ~1e-16 relative error: with t = -h / range,
+// t = k ln2/64 + r (|r| <= ln2/128), exp(t) = 2^(k >> 6) * 2^((k & 63)/64) * P5(r); psill is folded into the
+// coefficients of P5, the power-of-two table lives in shared memory.  Branch-free: 10 FP64 operations, one table
+// lookup and five integer operations per value (this is a third of all the instructions of the kriging kernel).
+constexpr int KED_TABN = 64;
+struct CovPar {
+    double c00;                      // C(0) = nugget + partial sill
+    double nir, nk;                  // -1/range and -64/(range ln2); 0 for the pure nugget model
+    double c0, c2, c3, c4, c5;       // psill * {1, 1/2, 1/6, 1/24, 1/120} (0 for the pure nugget model)
+};
+__device__ __forceinline__ void covpar_set(CovPar& cp, double nug, double psill, double rng) {
+    cp.c00 = nug + psill;
+    // range == 0: pure nugget model, C(h > 0) = 0 (interp.R:223-227).  -1/range is clamped at -250 / km (a range of
+    // 4 m: every covariance between distinct stations is already zero) so that k stays inside 32 bits.
+    const bool nugget_only = !(rng != 0.0) || !(psill != 0.0);
+    const double nir = nugget_only ? 0.0 : fmax(-1.0 / rng, -250.0);
+    const double ps = nugget_only ? 0.0 : psill;
+    cp.nir = nir;
+    cp.nk = nir * 92.33248261689366;                          // 64 / ln2
+    cp.c0 = ps; cp.c2 = ps * 0.5; cp.c3 = ps * (1.0 / 6.0); cp.c4 = ps * (1.0 / 24.0); cp.c5 = ps * (1.0 / 120.0);
+}
+// C(h) for h > 0 (also the value the exponential model takes at h == 0, without the nugget)
+__device__ __forceinline__ double cov_pos(double h, const CovPar& cp, const double* __restrict__ tab) {
+#if TWXI_KED_FAKE == 2
+    return cp.c0 * (h * cp.nir);
+#else
+    const double SHIFT = 6755399441055744.0;                  // 2^52 + 2^51: rounds to nearest integer
+    double kd = fma(h, cp.nk, SHIFT);
+    int ki = __double2loint(kd);
+    kd -= SHIFT;
+    const double r = fma(kd, -0.010830424696249145, h * cp.nir);    // ln2/64; the product is exact inside the fma, and the
+                                                              // rounding of the constant costs |k| * 1.2e-18 (< 1e-15 for h < 12 ranges)
+    double p = fma(r, cp.c5, cp.c4);
+    p = fma(r, p, cp.c3);
+    p = fma(r, p, cp.c2);
+    p = fma(r, p, cp.c0);
+    p = fma(r, p, cp.c0);
+    ki = max(ki, -KED_TABN * 1000);                                // below 2^-1000 the value does not matter, the exponent must stay valid
+    const double v = p * tab[ki & (KED_TABN - 1)];
+    return __hiloint2double(__double2hiint(v) + ((ki >> 6) << 20), __double2loint(v));
+#endif
+}
+// C(h) of a pair that may be co-located (point - station): nug+psill at h == 0
+__device__ __forceinline__ double cov(double h, const CovPar& cp, const double* tab) {
+    const double e = cov_pos(h, cp, tab);
+    return h == 0.0 ? cp.c00 : e;
+}
+// V tile (I, K) from its distance tile in C-fragment layout; lane holds (i, j) and (i, j+1).
+// `plain` (warp-uniform): the tile is strictly below the diagonal and inside the n x n block, so no masking.
+__device__ __forceinline__ double2 cov_tile(double2 h, int i, int j, int n, const CovPar& cp, const double* tab32,
+                                            bool plain) {
+    double2 v;                                                // (co-located station pairs never get here: hgather)
+    v.x = cov_pos(h.x, cp, tab32);
+    v.y = cov_pos(h.y, cp, tab32);
+    if (!plain) {                                             // diagonal tiles are kept fully symmetric (elim8_mma)
+        if (j == i) v.x = cp.c00;
+        if (j + 1 == i) v.y = cp.c00;
+        if (i >= n || j >= n) v.x = (i == j) ? 1.0 : 0.0;     // identity padding
+        if (i >= n || j + 1 >= n) v.y = (i == j + 1) ? 1.0 : 0.0;
+    }
+    return v;
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* mbar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void* mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* mbar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_u32(mbar)), "r"(parity) : "memory");
+    } while (!done);
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on the mbarrier (bytes and addresses multiples of 16)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, void* mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
+}
+
+// 5x5 GLS from S = B'V^-1B held by one warp in C-fragment layout: mean and variance of the kriging predictor.
+// S = [[G, g_y, g_c], [., ., s_cy], [., ., s_cc]] (row/column 7 are padding).  Bordering G with g_y and -(x0 - g_c)
+// (x0 = e_0: the drift columns are centred on the prediction point) and eliminating its 5 pivots leaves
+//     T[5][6] = s_cy + g_y' G^-1 (x0 - g_c) = mean - yref,     T[6][6] = -(x0 - g_c)' G^-1 (x0 - g_c),
+// so var = C(0) - s_cc - T[6][6].  The elimination runs on the tensor pipe like the pivot tiles (elim8_mma).
+__device__ __forceinline__ void ked_finish(double* mean_out, double* var_out, int32_t* status, double2 s0, int q, int m,
+                                           double yref, double c00, int lane) {
+    const double scc = s0.x;                                  // S[6][6] in lane 27
+    if (lane == 4 * 6 + 0 || lane == 4 * 0 + 3) s0.x -= 1.0;  // (6,0) and (0,6): g_c - x0
+    if (lane == 4 * 6 + 3) s0.x = 0.0;                        // (6,6)
+    const bool ok = elim8_mma<5>(s0, lane);
+    const double t56 = __shfl_sync(0xffffffffu, s0.x, 4 * 5 + 3);
+    if (lane == 4 * 6 + 3) {
+        const double mean = t56 + yref, var = c00 - scc - s0.x;
+        if (!ok || !isfinite(mean) || !isfinite(var)) {
+            atomicCAS(status + q, TWXI_ST_OK, TWXI_ST_SINGULAR);
+        } else {
+            mean_out[(size_t)q * 12 + m] = mean;
+            var_out[(size_t)q * 12 + m] = var;
+        }
+    }
+}
+
+// ked_warp.cu
+typedef void (*KedKernelFn)(KedArgs);
+KedKernelFn ked_warp_variant(int i, int* nmax);
+size_t ked_warp_smem_for(int nbv);
+
+}  // namespace twxi

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtwxi.so")
-SOURCES = ["api.cu", "knn.cu", "setup.cu", "ked.cu", "ked_warp.cu", "gwr.cu", "fixer.cu", "peak.cu"]
+SOURCES = ["api.cu", "knn.cu", "setup.cu", "ked.cu", "ked_warp.cu", "ked_rl.cu", "gwr.cu", "fixer.cu", "peak.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--use_fast_math=false"]
 NVCC_FLAGS = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]   # never fast-math: FP64 parity

@@ -505,6 +505,10 @@ struct KedWork {                 // device scratch of the kriging stage, owned p
     int sms = 0;
     int occ[16][KED_MAXNB + 1];   // resident CTAs per SM for (variant, size class)
     int var_for[KED_MAXNB + 1];  // variant chosen for each size class
+    // right-looking register-resident kernel (ked_rl.cu), per size class: kernel (nullptr: use the variant above)
+    KedKernelFn rl_fn[KED_MAXNB + 1];
+    int rl_threads[KED_MAXNB + 1], rl_occ[KED_MAXNB + 1];
+    size_t rl_smem[KED_MAXNB + 1];
 };
 
 // Launch variants: NW worker warps + the diagonal warp, minimum resident CTAs (register cap), largest n served.
@@ -587,6 +591,29 @@ int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
             if (KED_VARIANTS[v].nmax < 8 * nb) v = 5;
             w.var_for[nb] = v;
         }
+        // TWXI_KED_RL: "0" none, "1" every instantiated class, or a comma list of size classes; default = measured choice
+        {
+            static const char* rl_dflt = "0";
+            const char* e = getenv("TWXI_KED_RL");
+            if (!e || !*e) e = rl_dflt;
+            const bool all = !strcmp(e, "1") || !strcmp(e, "all");
+            bool want[KED_MAXNB + 1] = {false};
+            if (!all)
+                for (const char* c2 = e; *c2;) {
+                    const int v = atoi(c2);
+                    if (v >= 1 && v <= KED_MAXNB) want[v] = true;
+                    while (*c2 && *c2 != ',') ++c2;
+                    if (*c2 == ',') ++c2;
+                }
+            for (int nb = 0; nb <= KED_MAXNB; ++nb) {
+                w.rl_fn[nb] = nullptr;
+                KedKernelFn fn; int th; size_t sm;
+                if (nb < 1 || !(all || want[nb]) || !ked_rl_lookup(nb, &fn, &th, &sm)) continue;
+                int o = 0;
+                TWXI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, fn, th, sm));
+                w.rl_fn[nb] = fn; w.rl_threads[nb] = th; w.rl_smem[nb] = sm; w.rl_occ[nb] = std::max(1, o);
+            }
+        }
         w.sms = p.multiProcessorCount;
     }
     const int nbmax = (b.k1 - 1 + 7) / 8;                    // largest possible n is k1 - 1
@@ -647,6 +674,12 @@ int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
         // largest classes first: they are the long poles
         for (int nbv = nbmax; nbv >= 1; --nbv) {
             a.nbv = nbv;
+            if (w.rl_fn[nbv]) {
+                const int grid = std::min(w.sms * w.rl_occ[nbv], std::max(1, nt));
+                w.rl_fn[nbv]<<<grid, w.rl_threads[nbv], w.rl_smem[nbv], c.stream>>>(a);
+                TWXI_LAUNCH_CHECK();
+                continue;
+            }
             const int v = w.var_for[nbv];
             const size_t smem = KED_VARIANTS[v].nw ? ked_smem_for(nbv) : ked_warp_smem_for(nbv);
             const int grid = std::min(w.sms * w.occ[v][nbv], std::max(1, nt));

@@ -130,6 +130,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
 }
 
+// 16-byte asynchronous copy global -> shared (lane-private slots: the issuing lane is the only reader)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // 5x5 GLS from S = B'V^-1B held by one warp in C-fragment layout: mean and variance of the kriging predictor.
 // S = [[G, g_y, g_c], [., ., s_cy], [., ., s_cc]] (row/column 7 are padding).  Bordering G with g_y and -(x0 - g_c)
 // (x0 = e_0: the drift columns are centred on the prediction point) and eliminating its 5 pivots leaves
@@ -157,5 +164,7 @@ __device__ __forceinline__ void ked_finish(double* mean_out, double* var_out, in
 typedef void (*KedKernelFn)(KedArgs);
 KedKernelFn ked_warp_variant(int i, int* nmax);
 size_t ked_warp_smem_for(int nbv);
+// ked_rl.cu: right-looking register-resident kernel of size class nbv (false: not instantiated)
+bool ked_rl_lookup(int nbv, KedKernelFn* fn, int* threads, size_t* smem);
 
 }  // namespace twxi

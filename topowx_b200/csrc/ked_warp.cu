@@ -32,11 +32,6 @@ __host__ __device__ inline int kw_ring_slots(int nb) {          // ring slots of
 }
 __host__ __device__ inline int kw_tab_doubles(int nb) { return (((nb + 1) * nb * 2 + 15) / 16) * 2; }
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 struct WChain {
     double2 a, z;

@@ -31,6 +31,8 @@ struct KedArgs {
     const int32_t* bstart;     // [KED_MAXNB+1]
     const int32_t* bcount;
     int nbv;                   // size class of this launch
+    int rot_sms;               // > 0: warp roles rotate with blockIdx.x / rot_sms (the CTA's residency slot on its SM), so that
+                               // the diagonal warps of the CTAs of one SM sit on different SM sub-partitions
     double* mean;              // [npts][12]
     double* var;
     int32_t* status;
@@ -135,7 +137,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // 5x5 GLS from S = B'V^-1B held by one warp in C-fragment layout: mean and variance of the kriging predictor.
 // S = [[G, g_y, g_c], [., ., s_cy], [., ., s_cc]] (row/column 7 are padding).  Bordering G with g_y and -(x0 - g_c)

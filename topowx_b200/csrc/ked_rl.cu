@@ -28,11 +28,14 @@ namespace twxi {
 
 constexpr int RL_HDR = 64 + 2 * 64;               // doubles: 2^(j/64), -inv(L_KK) x2
 // shared memory (doubles): header | panel [2][NB+1] tiles | pivot tiles [2][NB+1] (double-buffered by problem) |
-// staging [NB(NB+1)/2] tiles (slot ltile(I,J)); every tile is 64 doubles in fragment layout (lane-private double2)
+// staging [NB(NB+1)/2] tiles (slot ltile(I,J)) | neighbour indices of the augmented rows | variogram parameters;
+// every tile is 64 doubles in fragment layout (lane-private double2)
 __host__ __device__ constexpr int rl_off_panel(int) { return RL_HDR; }
 __host__ __device__ constexpr int rl_off_diag(int NB) { return RL_HDR + 2 * (NB + 1) * 64; }
 __host__ __device__ constexpr int rl_off_stage(int NB) { return RL_HDR + 4 * (NB + 1) * 64; }
-__host__ __device__ constexpr int rl_smem_doubles(int NB) { return rl_off_stage(NB) + NB * (NB + 1) / 2 * 64; }
+__host__ __device__ constexpr int rl_off_idx(int NB) { return rl_off_stage(NB) + NB * (NB + 1) / 2 * 64; }   // [NB][32] int2 (one double each)
+__host__ __device__ constexpr int rl_off_vario(int NB) { return rl_off_idx(NB) + NB * 32; }                  // [warps][32][4] doubles
+__host__ __device__ constexpr int rl_smem_doubles(int NB, int NW) { return rl_off_vario(NB) + (NW + 1) * 128; }
 
 // owner of tile row I (1..NB; row NB = the augmented rows): snake over the rows in order of decreasing length
 __host__ __device__ constexpr int rl_owner(int NB, int NW, int I) {
@@ -44,15 +47,34 @@ __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+
 struct RlProb {
     int q, m, n;
     double nug, psill, rng;
 };
-__device__ __forceinline__ RlProb rl_load_prob(const KedArgs& a, int2 desc) {
+// variogram parameters of a problem -> the lane's private slot (asynchronously, one problem ahead), and back
+__device__ __forceinline__ void rl_prefetch_vario(const KedArgs& a, int2 desc, double* slot) {
+    const int q = desc.x / 12, m = desc.x - q * 12;
+    const double* vp = a.vario_is_override ? a.vario + (size_t)q * 3 : a.vario + ((size_t)q * 12 + m) * 3;
+    cp_async8(slot, vp); cp_async8(slot + 1, vp + 1); cp_async8(slot + 2, vp + 2);
+}
+__device__ __forceinline__ RlProb rl_load_prob_g(const KedArgs& a, int2 desc) {
     RlProb p;
     p.q = desc.x / 12; p.m = desc.x - p.q * 12; p.n = desc.y;
     const double* vp = a.vario_is_override ? a.vario + (size_t)p.q * 3 : a.vario + ((size_t)p.q * 12 + p.m) * 3;
     p.nug = vp[0]; p.psill = vp[1]; p.rng = vp[2];
+    return p;
+}
+__device__ __forceinline__ RlProb rl_load_prob(int2 desc, const double* slot) {      // after cp_async_wait_all
+    RlProb p;
+    p.q = desc.x / 12; p.m = desc.x - p.q * 12; p.n = desc.y;
+    p.nug = slot[0]; p.psill = slot[1]; p.rng = slot[2];
     return p;
 }
 __device__ __forceinline__ const double2* rl_hc2(const KedArgs& a, int2 desc, int lane) {
@@ -92,7 +114,54 @@ __device__ __noinline__ void rl_prefetch_rows(const double2* hc2, double2* stage
     cp_async_commit();
 }
 
-// staging slots of worker W: raw distances -> -C(h); augmented rows -B' gathered in fragment layout
+// Augmented rows -B' = -[1, dlon, dlat, delev, dlst, y - yref, c0, 0]' of the NEXT problem, fetched by their owner during
+// the stage loop of the current one.  Lane (r8, q4) holds row r8 of the stations 8J + 2 q4, + 1.  Two steps, both
+// asynchronous, because the gather addresses depend on the neighbour indices: (1) indices -> shared memory,
+// (2) station values -> the staging slots of tile row NB.  (Gathering them with plain loads at the start of a problem
+// serialises ~2 NB dependent global loads behind divergent branches: 25 k cycles during which every other warp waits.)
+template <int NB>
+__device__ __noinline__ void rl_bprime_idx(const KedArgs& a, int2 desc, double* sm, int lane) {
+    const int q4 = lane & 3, n = desc.y;
+    const int32_t* ip = a.idx + (size_t)(desc.x / 12) * a.k1;
+    int32_t* ist = reinterpret_cast<int32_t*>(sm + rl_off_idx(NB)) + 2 * lane;
+#pragma unroll 4
+    for (int J = 0; J < NB; ++J) {
+        const int j0 = 8 * J + 2 * q4;
+        cp_async4(ist + J * 64, ip + (j0 < n ? j0 : 0));
+        cp_async4(ist + J * 64 + 1, ip + (j0 + 1 < n ? j0 + 1 : 0));
+    }
+    cp_async_commit();
+}
+template <int NB>
+__device__ __noinline__ void rl_bprime_gather(const KedArgs& a, int2 desc, double* sm, int lane) {
+    const int r8 = lane >> 2, q4 = lane & 3, n = desc.y;
+    const int q = desc.x / 12, m = desc.x - q * 12, N = a.st.n;
+    const int32_t* ist = reinterpret_cast<const int32_t*>(sm + rl_off_idx(NB)) + 2 * lane;
+    double* brow = sm + rl_off_stage(NB) + ltile(NB, 0) * 64 + 2 * lane;
+    const double* src = r8 == 1 ? a.st.lon : r8 == 2 ? a.st.lat : r8 == 3 ? a.st.elev
+                      : r8 == 4 ? a.st.lst + (size_t)m * N : a.st.norm + (size_t)m * N;
+    const double* h0 = a.h0 + (size_t)q * a.k1;
+    cp_async_wait_all();                                      // the indices have landed
+    if (r8 >= 1 && r8 <= 5) {
+#pragma unroll 4
+        for (int J = 0; J < NB; ++J) {
+            cp_async8(brow + J * 64, src + ist[J * 64]);
+            cp_async8(brow + J * 64 + 1, src + ist[J * 64 + 1]);
+        }
+    } else if (r8 == 6) {
+#pragma unroll 4
+        for (int J = 0; J < NB; ++J) {
+            const int j0 = 8 * J + 2 * q4;
+            cp_async8(brow + J * 64, h0 + (j0 < n ? j0 : 0));
+            cp_async8(brow + J * 64 + 1, h0 + (j0 + 1 < n ? j0 + 1 : 0));
+        }
+    } else if (lane == 0) {                                   // y_ref = normal of the nearest station, travels in lane 0's slot
+        cp_async8(brow, a.st.norm + (size_t)m * N + ist[0]);
+    }
+    cp_async_commit();
+}
+
+// staging slots of worker W: raw distances -> -C(h); raw station values -> augmented rows
 template <int NB, int NW>
 __device__ __noinline__ void rl_prologue(const KedArgs& a, const RlProb& p, double* sm, int lane, int W) {
     const int r8 = lane >> 2, q4 = lane & 3, n = p.n;
@@ -100,47 +169,26 @@ __device__ __noinline__ void rl_prologue(const KedArgs& a, const RlProb& p, doub
     double2* stage2 = reinterpret_cast<double2*>(sm + rl_off_stage(NB)) + lane;
     CovPar cp;
     covpar_set(cp, p.nug, p.psill, p.rng);
-    // -B' = -[1, dlon, dlat, delev, dlst, y - yref, c0, 0]': lane (r8, q4) holds row r8 of the stations 8J + 2 q4, + 1
     if (W == rl_owner(NB, NW, NB)) {
-        const int N = a.st.n;
-        const int32_t* ip = a.idx + (size_t)p.q * a.k1;
-        const double* lstm = a.st.lst + (size_t)p.m * N;
-        const double* normm = a.st.norm + (size_t)p.m * N;
-        const double* h0 = a.h0 + (size_t)p.q * a.k1;
-        const int s_first = ip[0];
-        const double* src = r8 == 1 ? a.st.lon : r8 == 2 ? a.st.lat : r8 == 3 ? a.st.elev : r8 == 4 ? lstm : normm;
+        // y_ref travels in lane 0's slot of tile (NB, 0); lanes with r8 == 5 need it
+        const double yref = __shfl_sync(0xffffffffu, stage2[ltile(NB, 0) * 32].x, 0);
         const double x0 = r8 == 1 ? a.qlon[p.q] : r8 == 2 ? a.qlat[p.q] : r8 == 3 ? a.qelev[p.q]
-                        : r8 == 4 ? a.qlst[(size_t)p.q * 12 + p.m] : normm[s_first];
+                        : r8 == 4 ? a.qlst[(size_t)p.q * 12 + p.m] : yref;
         const double sc = r8 == 3 ? 1e-3 : r8 == 4 ? 0.1 : 1.0;
         const bool gath = r8 >= 1 && r8 <= 5;
-        double2 g[NB];
-#pragma unroll
-        for (int J = 0; J < NB; ++J) {                        // all gathers in flight at once
-            const int j0 = 8 * J + 2 * q4;
-            const bool in0 = j0 < n, in1 = j0 + 1 < n;
-            double vx = 0.0, vy = 0.0;
-            if (gath) {
-                const int s0 = in0 ? ip[j0] : s_first, s1 = in1 ? ip[j0 + 1] : s_first;
-                vx = src[s0]; vy = src[s1];
-            } else if (r8 == 6) {
-                vx = in0 ? h0[j0] : 1.0;
-                vy = in1 ? h0[j0 + 1] : 1.0;
-            }
-            g[J] = make_double2(vx, vy);
-        }
-#pragma unroll
+#pragma unroll 2
         for (int J = 0; J < NB; ++J) {
             const int j0 = 8 * J + 2 * q4;
-            double2 v = g[J];
+            double2 v = stage2[(ltile(NB, 0) + J) * 32];
             if (gath) { v.x = (x0 - v.x) * sc; v.y = (x0 - v.y) * sc; }
             else if (r8 == 6) { v.x = -cov(v.x, cp, tab32); v.y = -cov(v.y, cp, tab32); }
             else if (r8 == 0) { v.x = -1.0; v.y = -1.0; }
+            else { v.x = 0.0; v.y = 0.0; }
             if (j0 >= n) v.x = 0.0;
             if (j0 + 1 >= n) v.y = 0.0;
             stage2[(ltile(NB, 0) + J) * 32] = v;
         }
     }
-    cp_async_wait_all();                                      // the raw distance tiles of the owned rows have landed
     const bool full = 8 * NB <= n;                            // no identity padding in the last V row
 #pragma unroll 1
     for (int I = 1; I < NB; ++I) {
@@ -173,9 +221,17 @@ __device__ __forceinline__ void rl_worker(const KedArgs& a, double* sm, int lane
     int slot = blockIdx.x;
     if (slot >= count) return;
     int2 desc = a.list[start + slot];
+    double* vslot = sm + rl_off_vario(NB) + (W * 32 + lane) * 4;
+    constexpr bool BOWNER = rl_owner(NB, NW, NB) == W;        // this worker owns the augmented rows
     rl_prefetch_rows<NB, NW>(rl_hc2(a, desc, lane), stage2, W);
+    rl_prefetch_vario(a, desc, vslot);
+    if constexpr (BOWNER) {
+        rl_bprime_idx<NB>(a, desc, sm, lane);
+        rl_bprime_gather<NB>(a, desc, sm, lane);
+    }
     for (; slot < count; slot += gridDim.x) {
-        const RlProb p = rl_load_prob(a, desc);
+        cp_async_wait_all();                                  // this problem's tiles, station values and parameters have landed
+        const RlProb p = rl_load_prob(desc, vslot);
         const bool has_next = slot + (int)gridDim.x < count;
         if (has_next) desc = a.list[start + slot + gridDim.x];
         rl_prologue<NB, NW>(a, p, sm, lane, W);
@@ -187,8 +243,15 @@ __device__ __forceinline__ void rl_worker(const KedArgs& a, double* sm, int lane
 
         RL_FOR(K, 0, NB,
             named_bar_sync(1, NT);                            // -W_K published
-            if constexpr (K == 0) {                           // the staging slots are free: fetch the next problem's tiles
-                if (has_next) rl_prefetch_rows<NB, NW>(rl_hc2(a, desc, lane), stage2, W);
+            if constexpr (K == 0) {                           // the staging slots are free: fetch the next problem's inputs
+                if (has_next) {
+                    rl_prefetch_rows<NB, NW>(rl_hc2(a, desc, lane), stage2, W);
+                    rl_prefetch_vario(a, desc, vslot);
+                    if constexpr (BOWNER) rl_bprime_idx<NB>(a, desc, sm, lane);
+                }
+            }
+            if constexpr (K == 2 && BOWNER) {
+                if (has_next) rl_bprime_gather<NB>(a, desc, sm, lane);
             }
             const double2 negW = Wt2[(K & 1) * 32];
             // panel: L(I,K) = N(I,K)(-W)' for the owned rows, kept in registers (A operand) and published (B operand)
@@ -234,11 +297,15 @@ __device__ __forceinline__ void rl_diag(const KedArgs& a, double* sm, int lane, 
         for (int J = 0; J < NB; ++J) cp_async16(dgs2 + J * 32, hc2 + htile(J, J) * 32);
         cp_async_commit();
     }
+    RlProb pn = rl_load_prob_g(a, desc);
     for (int buf = 0; slot < count; slot += gridDim.x, buf ^= 1) {
-        const RlProb p = rl_load_prob(a, desc);
+        const RlProb p = pn;
         const int n = p.n;
         const bool has_next = slot + (int)gridDim.x < count;
-        if (has_next) desc = a.list[start + slot + gridDim.x];
+        if (has_next) {                                       // descriptor and parameters one problem ahead, in registers
+            desc = a.list[start + slot + gridDim.x];
+            pn = rl_load_prob_g(a, desc);
+        }
         const double yref = a.st.norm[(size_t)p.m * N + a.idx[(size_t)p.q * a.k1]];
         CovPar cp;
         covpar_set(cp, p.nug, p.psill, p.rng);
@@ -262,7 +329,6 @@ __device__ __forceinline__ void rl_diag(const KedArgs& a, double* sm, int lane, 
                 Wd[16 * q4 + r8] = -zt.x;
                 Wd[16 * q4 + 8 + r8] = -zt.y;
             }
-            __threadfence_block();
             named_bar_arrive(1, NT);
             if (K == 0) {                                     // the other pivot tiles: N(J,J) = -V(J,J); S tile = 0
 #pragma unroll 2
@@ -317,7 +383,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_rl_kernel(KedArgs a) 
     extern __shared__ __align__(16) double sm[];
     constexpr int NT = (NW + 1) * 32;
     const int tid = threadIdx.x, lane = tid & 31;
-    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    if (a.rot_sms > 0) warp = (warp + (int)blockIdx.x / a.rot_sms) % (NW + 1);      // role of this warp (NW = diagonal warp)
     const int count = a.bcount[NB], start = a.bstart[NB];
     for (int i = tid; i < KED_TABN; i += NT) sm[i] = exp2((double)i / KED_TABN);
     __syncthreads();
@@ -348,7 +415,7 @@ bool ked_rl_lookup(int nbv, KedKernelFn* fn, int* threads, size_t* smem) {
     if (!e.fn) return false;
     *fn = e.fn;
     *threads = (e.nw + 1) * 32;
-    *smem = (size_t)rl_smem_doubles(nbv) * sizeof(double);
+    *smem = (size_t)rl_smem_doubles(nbv, e.nw) * sizeof(double);
     return true;
 }
 

@@ -26,16 +26,17 @@
 
 namespace twxi {
 
-constexpr int RL_HDR = 64 + 2 * 64;               // doubles: 2^(j/64), -inv(L_KK) x2
-// shared memory (doubles): header | panel [2][NB+1] tiles | pivot tiles [2][NB+1] (double-buffered by problem) |
-// staging [NB(NB+1)/2] tiles (slot ltile(I,J)) | neighbour indices of the augmented rows | variogram parameters;
-// every tile is 64 doubles in fragment layout (lane-private double2)
+constexpr int RL_HDR = 64 + 2 * 64 + 8;           // doubles: 2^(j/64), -inv(L_KK) x2, singular flags (by problem parity)
+// shared memory (doubles; every tile is 64 doubles in fragment layout = one lane-private double2 per lane):
+//   header | panel [2][NB+1] tiles | live pivot tiles N(I,I) [NB+1] | staging (NB+1)(NB+2)/2 tiles, slot htile(I,J):
+//   rows 0..NB-1 = V with its diagonal tiles, row NB = the augmented rows | neighbour indices of the augmented rows
+//   [NB][32] int2 | per warp 16 doubles: variogram parameters (3), CovPar (8) of the next problem, y_ref, C(0)
 __host__ __device__ constexpr int rl_off_panel(int) { return RL_HDR; }
-__host__ __device__ constexpr int rl_off_diag(int NB) { return RL_HDR + 2 * (NB + 1) * 64; }
-__host__ __device__ constexpr int rl_off_stage(int NB) { return RL_HDR + 4 * (NB + 1) * 64; }
-__host__ __device__ constexpr int rl_off_idx(int NB) { return rl_off_stage(NB) + NB * (NB + 1) / 2 * 64; }   // [NB][32] int2 (one double each)
-__host__ __device__ constexpr int rl_off_vario(int NB) { return rl_off_idx(NB) + NB * 32; }                  // [warps][32][4] doubles
-__host__ __device__ constexpr int rl_smem_doubles(int NB, int NW) { return rl_off_vario(NB) + (NW + 1) * 128; }
+__host__ __device__ constexpr int rl_off_dlive(int NB) { return RL_HDR + 2 * (NB + 1) * 64; }
+__host__ __device__ constexpr int rl_off_stage(int NB) { return RL_HDR + 3 * (NB + 1) * 64; }
+__host__ __device__ constexpr int rl_off_idx(int NB) { return rl_off_stage(NB) + (NB + 1) * (NB + 2) / 2 * 64; }
+__host__ __device__ constexpr int rl_off_warp(int NB) { return rl_off_idx(NB) + NB * 32; }
+__host__ __device__ constexpr int rl_smem_doubles(int NB, int NW) { return rl_off_warp(NB) + (NW + 1) * 16; }
 
 // owner of tile row I (1..NB; row NB = the augmented rows): snake over the rows in order of decreasing length
 __host__ __device__ constexpr int rl_owner(int NB, int NW, int I) {
@@ -46,7 +47,6 @@ __host__ __device__ constexpr int rl_owner(int NB, int NW, int I) {
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
@@ -54,31 +54,21 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 
-struct RlProb {
-    int q, m, n;
-    double nug, psill, rng;
-};
-// variogram parameters of a problem -> the lane's private slot (asynchronously, one problem ahead), and back
-__device__ __forceinline__ void rl_prefetch_vario(const KedArgs& a, int2 desc, double* slot) {
+__device__ __forceinline__ const double* rl_vario_ptr(const KedArgs& a, int2 desc) {
     const int q = desc.x / 12, m = desc.x - q * 12;
-    const double* vp = a.vario_is_override ? a.vario + (size_t)q * 3 : a.vario + ((size_t)q * 12 + m) * 3;
-    cp_async8(slot, vp); cp_async8(slot + 1, vp + 1); cp_async8(slot + 2, vp + 2);
-}
-__device__ __forceinline__ RlProb rl_load_prob_g(const KedArgs& a, int2 desc) {
-    RlProb p;
-    p.q = desc.x / 12; p.m = desc.x - p.q * 12; p.n = desc.y;
-    const double* vp = a.vario_is_override ? a.vario + (size_t)p.q * 3 : a.vario + ((size_t)p.q * 12 + p.m) * 3;
-    p.nug = vp[0]; p.psill = vp[1]; p.rng = vp[2];
-    return p;
-}
-__device__ __forceinline__ RlProb rl_load_prob(int2 desc, const double* slot) {      // after cp_async_wait_all
-    RlProb p;
-    p.q = desc.x / 12; p.m = desc.x - p.q * 12; p.n = desc.y;
-    p.nug = slot[0]; p.psill = slot[1]; p.rng = slot[2];
-    return p;
+    return a.vario_is_override ? a.vario + (size_t)q * 3 : a.vario + ((size_t)q * 12 + m) * 3;
 }
 __device__ __forceinline__ const double2* rl_hc2(const KedArgs& a, int2 desc, int lane) {
     return reinterpret_cast<const double2*>(a.hc + (size_t)(desc.x / 12 - a.q0) * a.hc_stride) + lane;
+}
+// CovPar <-> 8 doubles of shared memory (warp-uniform values)
+__device__ __forceinline__ void rl_cp_store(double* w, const CovPar& c) {
+    w[0] = c.c00; w[1] = c.nir; w[2] = c.nk; w[3] = c.c0; w[4] = c.c2; w[5] = c.c3; w[6] = c.c4; w[7] = c.c5;
+}
+__device__ __forceinline__ CovPar rl_cp_load(const double* w) {
+    CovPar c;
+    c.c00 = w[0]; c.nir = w[1]; c.nk = w[2]; c.c0 = w[3]; c.c2 = w[4]; c.c3 = w[5]; c.c4 = w[6]; c.c5 = w[7];
+    return c;
 }
 
 // compile-time loop: f(std::integral_constant<int, i>) for i = B..E-1.  The stage loop of the workers must be unrolled
@@ -98,27 +88,50 @@ __host__ __device__ constexpr bool rl_owns_below(int I = J + 1) {               
 }
 
 // Everything outside the unrolled stage loop is ROLLED code shared by all workers (run-time W): the whole kernel has to
-// stay within the 32 KB of the SM's instruction cache (a fully unrolled prologue made it 125 KB and 2x slower).
+// stay close to the 32 KB of the SM's instruction cache (a fully unrolled prologue made it 125 KB and 2x slower).
 
-// raw distance tiles of the rows owned by worker W -> their staging slots, asynchronously (lane-private 16 bytes)
+// raw distance tiles (with the diagonal tile) of the V rows owned by worker W -> staging, asynchronously
 template <int NB, int NW>
 __device__ __noinline__ void rl_prefetch_rows(const double2* hc2, double2* stage2, int W) {
 #pragma unroll 1
     for (int I = 1; I < NB; ++I) {
         if (rl_owner(NB, NW, I) != W) continue;
         const double2* src = hc2 + htile(I, 0) * 32;
-        double2* dst = stage2 + ltile(I, 0) * 32;
+        double2* dst = stage2 + htile(I, 0) * 32;
 #pragma unroll 4
-        for (int J = 0; J < I; ++J) cp_async16(dst + J * 32, src + J * 32);
+        for (int J = 0; J <= I; ++J) cp_async16(dst + J * 32, src + J * 32);
     }
     cp_async_commit();
 }
 
+// staging row I (1..NB-1): raw distances -> N = -V, including the diagonal tile
+template <int NB>
+__device__ __noinline__ void rl_cov_row(double* sm, int lane, int I, int n, const double* cpw) {
+    const int r8 = lane >> 2, q4 = lane & 3;
+    const double* tab32 = sm;
+    const CovPar cp = rl_cp_load(cpw);
+    double2* row = reinterpret_cast<double2*>(sm + rl_off_stage(NB)) + lane + htile(I, 0) * 32;
+    const bool plain = I < NB - 1 || 8 * NB <= n;             // no identity padding in this row
+    int J = 0;
+    for (; J + 1 < I; J += 2) {
+        const double2 h1 = row[J * 32], h2 = row[J * 32 + 32];
+        const double2 v1 = cov_tile(h1, 8 * I + r8, 8 * J + 2 * q4, n, cp, tab32, plain);
+        const double2 v2 = cov_tile(h2, 8 * I + r8, 8 * J + 8 + 2 * q4, n, cp, tab32, plain);
+        row[J * 32] = make_double2(-v1.x, -v1.y);
+        row[J * 32 + 32] = make_double2(-v2.x, -v2.y);
+    }
+    for (; J <= I; ++J) {                                     // last off-diagonal tile (I odd) and the diagonal tile
+        const double2 v1 = cov_tile(row[J * 32], 8 * I + r8, 8 * J + 2 * q4, n, cp, tab32, plain && J < I);
+        row[J * 32] = make_double2(-v1.x, -v1.y);
+    }
+}
+
 // Augmented rows -B' = -[1, dlon, dlat, delev, dlst, y - yref, c0, 0]' of the NEXT problem, fetched by their owner during
-// the stage loop of the current one.  Lane (r8, q4) holds row r8 of the stations 8J + 2 q4, + 1.  Two steps, both
-// asynchronous, because the gather addresses depend on the neighbour indices: (1) indices -> shared memory,
-// (2) station values -> the staging slots of tile row NB.  (Gathering them with plain loads at the start of a problem
-// serialises ~2 NB dependent global loads behind divergent branches: 25 k cycles during which every other warp waits.)
+// the stage loop of the current one.  Lane (r8, q4) holds row r8 of the stations 8J + 2 q4, + 1.  Two asynchronous
+// steps, because the gather addresses depend on the neighbour indices: (1) indices -> shared memory, (2) station values
+// -> the staging slots of tile row NB; then (3) the values are turned into the rows.  (Gathering them with plain loads at
+// the start of a problem serialises ~2 NB dependent global loads behind divergent branches: 25 k cycles during which
+// every other warp of the CTA waits.)
 template <int NB>
 __device__ __noinline__ void rl_bprime_idx(const KedArgs& a, int2 desc, double* sm, int lane) {
     const int q4 = lane & 3, n = desc.y;
@@ -137,7 +150,7 @@ __device__ __noinline__ void rl_bprime_gather(const KedArgs& a, int2 desc, doubl
     const int r8 = lane >> 2, q4 = lane & 3, n = desc.y;
     const int q = desc.x / 12, m = desc.x - q * 12, N = a.st.n;
     const int32_t* ist = reinterpret_cast<const int32_t*>(sm + rl_off_idx(NB)) + 2 * lane;
-    double* brow = sm + rl_off_stage(NB) + ltile(NB, 0) * 64 + 2 * lane;
+    double* brow = sm + rl_off_stage(NB) + htile(NB, 0) * 64 + 2 * lane;
     const double* src = r8 == 1 ? a.st.lon : r8 == 2 ? a.st.lat : r8 == 3 ? a.st.elev
                       : r8 == 4 ? a.st.lst + (size_t)m * N : a.st.norm + (size_t)m * N;
     const double* h0 = a.h0 + (size_t)q * a.k1;
@@ -160,109 +173,110 @@ __device__ __noinline__ void rl_bprime_gather(const KedArgs& a, int2 desc, doubl
     }
     cp_async_commit();
 }
-
-// staging slots of worker W: raw distances -> -C(h); raw station values -> augmented rows
-template <int NB, int NW>
-__device__ __noinline__ void rl_prologue(const KedArgs& a, const RlProb& p, double* sm, int lane, int W) {
-    const int r8 = lane >> 2, q4 = lane & 3, n = p.n;
+template <int NB>
+__device__ __noinline__ void rl_bprime_transform(const KedArgs& a, int2 desc, double* sm, int lane, double* wslot) {
+    const int r8 = lane >> 2, q4 = lane & 3, n = desc.y;
+    const int q = desc.x / 12, m = desc.x - q * 12;
     const double* tab32 = sm;
-    double2* stage2 = reinterpret_cast<double2*>(sm + rl_off_stage(NB)) + lane;
-    CovPar cp;
-    covpar_set(cp, p.nug, p.psill, p.rng);
-    if (W == rl_owner(NB, NW, NB)) {
-        // y_ref travels in lane 0's slot of tile (NB, 0); lanes with r8 == 5 need it
-        const double yref = __shfl_sync(0xffffffffu, stage2[ltile(NB, 0) * 32].x, 0);
-        const double x0 = r8 == 1 ? a.qlon[p.q] : r8 == 2 ? a.qlat[p.q] : r8 == 3 ? a.qelev[p.q]
-                        : r8 == 4 ? a.qlst[(size_t)p.q * 12 + p.m] : yref;
-        const double sc = r8 == 3 ? 1e-3 : r8 == 4 ? 0.1 : 1.0;
-        const bool gath = r8 >= 1 && r8 <= 5;
+    const CovPar cp = rl_cp_load(wslot + 4);
+    double2* brow2 = reinterpret_cast<double2*>(sm + rl_off_stage(NB)) + lane + htile(NB, 0) * 32;
+    const double yref = __shfl_sync(0xffffffffu, brow2[0].x, 0);
+    const double x0 = r8 == 1 ? a.qlon[q] : r8 == 2 ? a.qlat[q] : r8 == 3 ? a.qelev[q]
+                    : r8 == 4 ? a.qlst[(size_t)q * 12 + m] : yref;
+    const double sc = r8 == 3 ? 1e-3 : r8 == 4 ? 0.1 : 1.0;
+    const bool gath = r8 >= 1 && r8 <= 5;
 #pragma unroll 2
-        for (int J = 0; J < NB; ++J) {
-            const int j0 = 8 * J + 2 * q4;
-            double2 v = stage2[(ltile(NB, 0) + J) * 32];
-            if (gath) { v.x = (x0 - v.x) * sc; v.y = (x0 - v.y) * sc; }
-            else if (r8 == 6) { v.x = -cov(v.x, cp, tab32); v.y = -cov(v.y, cp, tab32); }
-            else if (r8 == 0) { v.x = -1.0; v.y = -1.0; }
-            else { v.x = 0.0; v.y = 0.0; }
-            if (j0 >= n) v.x = 0.0;
-            if (j0 + 1 >= n) v.y = 0.0;
-            stage2[(ltile(NB, 0) + J) * 32] = v;
-        }
+    for (int J = 0; J < NB; ++J) {
+        const int j0 = 8 * J + 2 * q4;
+        double2 v = brow2[J * 32];
+        if (gath) { v.x = (x0 - v.x) * sc; v.y = (x0 - v.y) * sc; }
+        else if (r8 == 6) { v.x = -cov(v.x, cp, tab32); v.y = -cov(v.y, cp, tab32); }
+        else if (r8 == 0) { v.x = -1.0; v.y = -1.0; }
+        else { v.x = 0.0; v.y = 0.0; }
+        if (j0 >= n) v.x = 0.0;
+        if (j0 + 1 >= n) v.y = 0.0;
+        brow2[J * 32] = v;
     }
-    const bool full = 8 * NB <= n;                            // no identity padding in the last V row
-#pragma unroll 1
-    for (int I = 1; I < NB; ++I) {
-        if (rl_owner(NB, NW, I) != W) continue;
-        const bool plain = I < NB - 1 || full;
-        double2* row = stage2 + ltile(I, 0) * 32;
-        int J = 0;
-        for (; J + 1 < I; J += 2) {
-            const double2 h1 = row[J * 32], h2 = row[J * 32 + 32];
-            const double2 v1 = cov_tile(h1, 8 * I + r8, 8 * J + 2 * q4, n, cp, tab32, plain);
-            const double2 v2 = cov_tile(h2, 8 * I + r8, 8 * J + 8 + 2 * q4, n, cp, tab32, plain);
-            row[J * 32] = make_double2(-v1.x, -v1.y);
-            row[J * 32 + 32] = make_double2(-v2.x, -v2.y);
-        }
-        if (J < I) {
-            const double2 v1 = cov_tile(row[J * 32], 8 * I + r8, 8 * J + 2 * q4, n, cp, tab32, plain);
-            row[J * 32] = make_double2(-v1.x, -v1.y);
-        }
-    }
+    if (lane == 0) { wslot[12] = yref; wslot[13] = cp.c00; }
+    __syncwarp();
+}
+// variogram parameters of a problem -> CovPar in the warp's slot (after the asynchronous copies have landed)
+__device__ __noinline__ void rl_setcp(double* wslot, int lane) {
+    cp_async_wait_all();
+    __syncwarp();
+    CovPar cp;
+    covpar_set(cp, wslot[0], wslot[1], wslot[2]);
+    __syncwarp();
+    if (lane == 0) rl_cp_store(wslot + 4, cp);
+    __syncwarp();
 }
 
-// ---- worker warp W of NW: owns the rows I with rl_owner(NB, NW, I) == W ------------------------------------------------
+// ---- worker warp W of NW: owns the rows I with rl_owner(NB, NW, I) == W, their diagonal tiles included ---------------------
 template <int NB, int NW, int W>
 __device__ __forceinline__ void rl_worker(const KedArgs& a, double* sm, int lane, int start, int count) {
     constexpr int NT = (NW + 1) * 32;
+    constexpr bool BOWNER = rl_owner(NB, NW, NB) == W;        // this worker owns the augmented rows and finishes the problem
     const double2* Wt2 = reinterpret_cast<const double2*>(sm + 64) + lane;
+    int* flagp = reinterpret_cast<int*>(sm + 192);
     double2* panel2 = reinterpret_cast<double2*>(sm + rl_off_panel(NB)) + lane;   // tile (b, I) at panel2[(b * (NB+1) + I) * 32]
+    double2* dlive2 = reinterpret_cast<double2*>(sm + rl_off_dlive(NB)) + lane;
     double2* stage2 = reinterpret_cast<double2*>(sm + rl_off_stage(NB)) + lane;
+    double* wslot = sm + rl_off_warp(NB) + W * 16;
 
     int slot = blockIdx.x;
     if (slot >= count) return;
     int2 desc = a.list[start + slot];
-    double* vslot = sm + rl_off_vario(NB) + (W * 32 + lane) * 4;
-    constexpr bool BOWNER = rl_owner(NB, NW, NB) == W;        // this worker owns the augmented rows
+    // first problem: the whole input pipeline up front
     rl_prefetch_rows<NB, NW>(rl_hc2(a, desc, lane), stage2, W);
-    rl_prefetch_vario(a, desc, vslot);
+    if (lane < 3) cp_async8(wslot + lane, rl_vario_ptr(a, desc) + lane);
     if constexpr (BOWNER) {
         rl_bprime_idx<NB>(a, desc, sm, lane);
         rl_bprime_gather<NB>(a, desc, sm, lane);
     }
-    for (; slot < count; slot += gridDim.x) {
-        cp_async_wait_all();                                  // this problem's tiles, station values and parameters have landed
-        const RlProb p = rl_load_prob(desc, vslot);
+    rl_setcp(wslot, lane);
+#pragma unroll 1
+    for (int I = 1; I < NB; ++I)
+        if (rl_owner(NB, NW, I) == W) rl_cov_row<NB>(sm, lane, I, desc.y, wslot + 4);
+    if constexpr (BOWNER) rl_bprime_transform<NB>(a, desc, sm, lane, wslot);
+
+    for (int par = 0;; par ^= 1) {
+        // the staging slots hold the tiles of problem `cur`, ready to use
+        const int2 cur = desc;
         const bool has_next = slot + (int)gridDim.x < count;
         if (has_next) desc = a.list[start + slot + gridDim.x];
-        rl_prologue<NB, NW>(a, p, sm, lane, W);
         double2 acc[NB * (NB + 1) / 2];
         RL_FOR(I, 1, NB + 1,
             if constexpr (rl_owner(NB, NW, I) == W) {
-                RL_FOR(J, 0, I, acc[ltile(I, J)] = stage2[ltile(I, J) * 32];);
+                RL_FOR(J, 0, I, acc[ltile(I, J)] = stage2[htile(I, J) * 32];);
+                if constexpr (I < NB) dlive2[I * 32] = stage2[htile(I, I) * 32];
+                else dlive2[I * 32] = make_double2(0.0, 0.0);
             });
+        double yref = 0.0, c00 = 0.0;
+        if constexpr (BOWNER) { yref = wslot[12]; c00 = wslot[13]; }
 
         RL_FOR(K, 0, NB,
             named_bar_sync(1, NT);                            // -W_K published
             if constexpr (K == 0) {                           // the staging slots are free: fetch the next problem's inputs
                 if (has_next) {
                     rl_prefetch_rows<NB, NW>(rl_hc2(a, desc, lane), stage2, W);
-                    rl_prefetch_vario(a, desc, vslot);
+                    if (lane < 3) cp_async8(wslot + lane, rl_vario_ptr(a, desc) + lane);
                     if constexpr (BOWNER) rl_bprime_idx<NB>(a, desc, sm, lane);
                 }
             }
-            if constexpr (K == 2 && BOWNER) {
-                if (has_next) rl_bprime_gather<NB>(a, desc, sm, lane);
-            }
             const double2 negW = Wt2[(K & 1) * 32];
-            // panel: L(I,K) = N(I,K)(-W)' for the owned rows, kept in registers (A operand) and published (B operand)
+            // panel: L(I,K) = N(I,K)(-W)' for the owned rows, kept in registers (A operand) and published (B operand);
+            // pivot tile of the row: N(I,I) += L(I,K) L(I,K)' (row K+1 first: the diagonal warp is waiting for it)
             RL_FOR(I, K + 1, NB + 1,
                 if constexpr (rl_owner(NB, NW, I) == W) {
                     double2 l = make_double2(0.0, 0.0);
                     dmma2(l, acc[ltile(I, K)], negW);
                     acc[ltile(I, K)] = l;
                     panel2[((K & 1) * (NB + 1) + I) * 32] = l;
+                    double2 d = dlive2[I * 32];
+                    dmma2(d, l, l);
+                    dlive2[I * 32] = d;
                 });
-            named_bar_sync(2, NT);                            // panel K complete
+            named_bar_sync(2, NT);                            // panel K and N(K+1,K+1) complete
             // trailing update, column K+1 first: N(I,J) += L(I,K) L(J,K)'
             RL_FOR(J, K + 1, NB,
                 if constexpr (rl_owns_below<NB, NW, W, J>()) {
@@ -272,53 +286,74 @@ __device__ __forceinline__ void rl_worker(const KedArgs& a, double* sm, int lane
                     RL_FOR(I, J + 1, NB + 1,
                         if constexpr (rl_owner(NB, NW, I) == W) dmma2(acc[ltile(I, J)], acc[ltile(I, K)], b););
                 });
+            // the next problem's covariance pass, spread over the stages (the workers wait for the diagonal warp anyway)
+            if (has_next) {
+                if constexpr (K == 2) {
+                    rl_setcp(wslot, lane);
+                    if constexpr (BOWNER) rl_bprime_gather<NB>(a, desc, sm, lane);
+                }
+                // one staging row per stage, by its owner (spreading every worker's tiles evenly over all stages was
+                // measured 1.5x slower: then every stage waits for a covariance chunk)
+                if constexpr (K >= 3 && rl_owner(NB, NW, K - 2) == W) {
+                    cp_async_wait_all();
+                    rl_cov_row<NB>(sm, lane, K - 2, desc.y, wslot + 4);
+                }
+                if constexpr (K == NB - 1) {
+                    cp_async_wait_all();
+                    if constexpr (rl_owner(NB, NW, NB - 2) == W) rl_cov_row<NB>(sm, lane, NB - 2, desc.y, wslot + 4);
+                    if constexpr (rl_owner(NB, NW, NB - 1) == W) rl_cov_row<NB>(sm, lane, NB - 1, desc.y, wslot + 4);
+                    if constexpr (BOWNER) rl_bprime_transform<NB>(a, desc, sm, lane, wslot);
+                }
+            }
         );
+        if constexpr (BOWNER) {                               // S = B'V^-1 B is this warp's pivot tile NB
+            const int q = cur.x / 12, m = cur.x - q * 12;
+            if (flagp[par]) {
+                if (lane == 0) atomicCAS(a.status + q, TWXI_ST_OK, TWXI_ST_SINGULAR);
+                __syncwarp();
+                if (lane == 0) flagp[par] = 0;
+            } else {
+                ked_finish(a.mean, a.var, a.status, dlive2[NB * 32], q, m, yref, c00, lane);
+            }
+        }
+        if (!has_next) break;
+        slot += gridDim.x;
     }
 }
 
-// ---- diagonal warp: owns the pivot tiles N(J,J), J = 0..NB (the last one ends up as S = B'V^-1 B); rolled code, the
-// tiles live in lane-private shared-memory slots, double-buffered so that the next problem's raw tiles are prefetched
+// ---- diagonal warp: nothing but the serial chain D_K -> -inv(L_KK), K = 0..NB-1 (rolled code) -----------------------------
 template <int NB, int NW>
 __device__ __forceinline__ void rl_diag(const KedArgs& a, double* sm, int lane, int start, int count) {
     constexpr int NT = (NW + 1) * 32;
     const int r8 = lane >> 2, q4 = lane & 3;
     const double* tab32 = sm;
     double* Wt = sm + 64;
-    const double2* panel2 = reinterpret_cast<const double2*>(sm + rl_off_panel(NB)) + lane;
-    double2* dgs2 = reinterpret_cast<double2*>(sm + rl_off_diag(NB)) + lane;
-    const int N = a.st.n;
+    int* flagp = reinterpret_cast<int*>(sm + 192);
+    const double2* dlive2 = reinterpret_cast<const double2*>(sm + rl_off_dlive(NB)) + lane;
+    double2* d0 = reinterpret_cast<double2*>(sm + rl_off_stage(NB)) + lane;      // staging slot of tile (0,0)
 
     int slot = blockIdx.x;
     if (slot >= count) return;
     int2 desc = a.list[start + slot];
+    if (lane < 2) flagp[lane] = 0;
     {
-        const double2* hc2 = rl_hc2(a, desc, lane);
-#pragma unroll 4
-        for (int J = 0; J < NB; ++J) cp_async16(dgs2 + J * 32, hc2 + htile(J, J) * 32);
-        cp_async_commit();
-    }
-    RlProb pn = rl_load_prob_g(a, desc);
-    for (int buf = 0; slot < count; slot += gridDim.x, buf ^= 1) {
-        const RlProb p = pn;
-        const int n = p.n;
-        const bool has_next = slot + (int)gridDim.x < count;
-        if (has_next) {                                       // descriptor and parameters one problem ahead, in registers
-            desc = a.list[start + slot + gridDim.x];
-            pn = rl_load_prob_g(a, desc);
-        }
-        const double yref = a.st.norm[(size_t)p.m * N + a.idx[(size_t)p.q * a.k1]];
+        const double* vp = rl_vario_ptr(a, desc);
         CovPar cp;
-        covpar_set(cp, p.nug, p.psill, p.rng);
-        double2* dg = dgs2 + buf * (NB + 1) * 32;
-        cp_async_wait_all();
-        if (has_next) {
-            const double2* hc2 = rl_hc2(a, desc, lane);
-            double2* dn = dgs2 + (buf ^ 1) * (NB + 1) * 32;
-#pragma unroll 4
-            for (int J = 0; J < NB; ++J) cp_async16(dn + J * 32, hc2 + htile(J, J) * 32);
+        covpar_set(cp, vp[0], vp[1], vp[2]);
+        d0[0] = cov_tile(rl_hc2(a, desc, lane)[0], r8, 2 * q4, desc.y, cp, tab32, false);      // V(0,0)
+    }
+    __syncwarp();
+    for (int par = 0;; par ^= 1) {
+        const bool has_next = slot + (int)gridDim.x < count;
+        double2 D = d0[0];
+        double nug = 0.0, psill = 0.0, rng = 0.0;
+        if (has_next) {                                       // next problem's tile (0,0) and parameters
+            desc = a.list[start + slot + gridDim.x];
+            cp_async16(d0, rl_hc2(a, desc, lane));
             cp_async_commit();
+            const double* vp = rl_vario_ptr(a, desc);
+            nug = vp[0]; psill = vp[1]; rng = vp[2];
         }
-        double2 D = cov_tile(dg[0], r8, 2 * q4, n, cp, tab32, false);       // V(0,0)
         bool ok = true;
 #pragma unroll 1
         for (int K = 0; K < NB; ++K) {
@@ -329,42 +364,20 @@ __device__ __forceinline__ void rl_diag(const KedArgs& a, double* sm, int lane, 
                 Wd[16 * q4 + r8] = -zt.x;
                 Wd[16 * q4 + 8 + r8] = -zt.y;
             }
+            if (!ok && lane == 0) flagp[par] = 1;
             named_bar_arrive(1, NT);
-            if (K == 0) {                                     // the other pivot tiles: N(J,J) = -V(J,J); S tile = 0
-#pragma unroll 2
-                for (int J = 1; J < NB; ++J) {
-                    const double2 v = cov_tile(dg[J * 32], 8 * J + r8, 8 * J + 2 * q4, n, cp, tab32, false);
-                    dg[J * 32] = make_double2(-v.x, -v.y);
-                }
-                dg[NB * 32] = make_double2(0.0, 0.0);
-            } else {                                          // pivot tiles K+1.. of stage K-1, from panel K-1 (still valid)
-                const double2* pp = panel2 + ((K - 1) & 1) * (NB + 1) * 32;
-                int J = K + 1;
-                for (; J + 2 <= NB; J += 3) {
-                    const double2 l0 = pp[J * 32], l1 = pp[J * 32 + 32], l2 = pp[J * 32 + 64];
-                    double2 d0 = dg[J * 32], d1 = dg[J * 32 + 32], d2 = dg[J * 32 + 64];
-                    dmma(d0, l0.x, l0.x); dmma(d1, l1.x, l1.x); dmma(d2, l2.x, l2.x);
-                    dmma(d0, l0.y, l0.y); dmma(d1, l1.y, l1.y); dmma(d2, l2.y, l2.y);
-                    dg[J * 32] = d0; dg[J * 32 + 32] = d1; dg[J * 32 + 64] = d2;
-                }
-                for (; J <= NB; ++J) {
-                    const double2 l0 = pp[J * 32];
-                    double2 d0 = dg[J * 32];
-                    dmma2(d0, l0, l0);
-                    dg[J * 32] = d0;
-                }
+            if (K == 1 && has_next) {                         // V(0,0) of the next problem, in the shadow of the workers' panel step
+                cp_async_wait_all();
+                CovPar cp;
+                covpar_set(cp, nug, psill, rng);
+                d0[0] = cov_tile(d0[0], r8, 2 * q4, desc.y, cp, tab32, false);
             }
-            named_bar_sync(2, NT);                            // panel K complete
-            const double2 l = panel2[((K & 1) * (NB + 1) + K + 1) * 32];
-            double2 d = dg[(K + 1) * 32];
-            dmma2(d, l, l);                                   // next pivot tile (the S tile for K+1 == NB) first
+            named_bar_sync(2, NT);                            // panel K and N(K+1,K+1) complete
+            const double2 d = dlive2[(K + 1) * 32];
             D = make_double2(-d.x, -d.y);
         }
-        if (!ok) {
-            if (lane == 0) atomicCAS(a.status + p.q, TWXI_ST_OK, TWXI_ST_SINGULAR);
-        } else {
-            ked_finish(a.mean, a.var, a.status, make_double2(-D.x, -D.y), p.q, p.m, yref, cp.c00, lane);
-        }
+        if (!has_next) break;
+        slot += gridDim.x;
     }
 }
 

@@ -275,8 +275,9 @@ __device__ __forceinline__ void rl_worker(const KedArgs& a, double* sm, int lane
                     double2 d = dlive2[I * 32];
                     dmma2(d, l, l);
                     dlive2[I * 32] = d;
+                    if constexpr (I == K + 1) named_bar_arrive(3, 64);      // next pivot tile ready: releases the diagonal warp
                 });
-            named_bar_sync(2, NT);                            // panel K and N(K+1,K+1) complete
+            named_bar_sync(2, NT - 32);                       // panel K complete (workers only)
             // trailing update, column K+1 first: N(I,J) += L(I,K) L(J,K)'
             RL_FOR(J, K + 1, NB,
                 if constexpr (rl_owns_below<NB, NW, W, J>()) {
@@ -372,7 +373,7 @@ __device__ __forceinline__ void rl_diag(const KedArgs& a, double* sm, int lane, 
                 covpar_set(cp, nug, psill, rng);
                 d0[0] = cov_tile(d0[0], r8, 2 * q4, desc.y, cp, tab32, false);
             }
-            named_bar_sync(2, NT);                            // panel K and N(K+1,K+1) complete
+            named_bar_sync(3, 64);                            // N(K+1,K+1) complete (signalled by the owner of row K+1 alone)
             const double2 d = dlive2[(K + 1) * 32];
             D = make_double2(-d.x, -d.y);
         }

@@ -1,4 +1,4 @@
-// Kriging stage, right-looking kernel with the trailing matrix in REGISTERS.
+// Kriging stage, right-looking kernel with the trailing matrix in REGISTERS (experimental, TWXI_KED_RL).
 //
 // Same problem, same tiles and the same DMMA building blocks as ked.cu (8x8 FP64 tiles in the mma C-fragment layout,
 // N := sum L L' - V so that DMMAs accumulate in place, -W = -inv(L_KK) from chol8_inverse_t), but the data flow is
@@ -7,20 +7,22 @@
 // what the shared-memory pipe delivers).  Here
 //   * tile ROWS are owned by worker warps (snake order over the row lengths, so that the tile counts balance) and the
 //     accumulators N(I,J) of an owned row never leave the owner's registers: the kernel is instantiated per size
-//     class NB and per warp, with the stage loop fully unrolled, so that every tile is a named register pair;
+//     class NB and per warp, with the stage loop unrolled by template recursion, so that every tile is a named register
+//     pair; the pivot tile N(I,I) of a row is kept by its owner too, in a lane-private shared-memory slot;
 //   * a stage K is:  diagonal warp  D_K -> -W_K (published, barrier 1);  owners  L(I,K) = N(I,K)(-W_K)' for their rows,
-//     published to a double-buffered PANEL in shared memory (barrier 2);  then every owner adds L(I,K) L(J,K)' to its
-//     tiles (I,J), J > K, column K+1 first: the A operand is the L(I,K) it has just computed (registers), the B operand
-//     is one LDS.128 per column shared by all owned rows -> ~0.35 shared-memory accesses per DMMA;
-//   * the diagonal warp owns all pivot tiles N(J,J); after barrier 2 it updates the next one, factorises it and
-//     publishes -W_{K+1} while the workers are still busy with the trailing update, then catches up on the other
-//     diagonals from the (still valid) panel K;
-//   * distance tiles go straight from the compact global buffer (hgather_kernel) into the accumulator registers of
-//     their owner, are turned into -C(h) there, and the augmented rows -B' are gathered by their owner directly in
-//     fragment layout: no TMA staging, no shared-memory copy of the matrix, no covariance pass behind a CTA barrier.
-// Shared memory per CTA falls from 30 KB (n ~ 76) to 12 KB; what bounds residency is the register file (~20 tiles per
-// worker).  A non-positive pivot does not change the control flow: the factorisation runs on with NaNs and the point is
-// flagged singular at the end.
+//     published to a double-buffered PANEL in shared memory, and N(I,I) += L(I,K) L(I,K)'; the owner of row K+1 does that
+//     row first and releases the diagonal warp (barrier 3), which factors D_{K+1} while the workers go on; barrier 2
+//     (workers only: panel K complete); then every owner adds L(I,K) L(J,K)' to its tiles (I,J), J > K, column K+1 first:
+//     the A operand is the L(I,K) it has just computed (registers), the B operand one LDS.128 per column shared by all
+//     owned rows;
+//   * the diagonal warp runs nothing but the pivot chain; the owner of the augmented rows also owns S = B'V^-1 B (pivot
+//     tile NB) and runs the 5x5 solve;
+//   * the inputs of the NEXT problem are fetched with cp.async into lane-private staging during the stage loop (distance
+//     tiles; neighbour indices, then station values of the augmented rows; variogram parameters) and turned into -C(h) /
+//     -B' there as well, one staging row per stage, so that a problem starts with plain LDS of finished tiles.
+// Everything outside the workers' stage loop is rolled code shared by all workers: the unrolled kernel has to stay near
+// the 32 KB of the instruction cache.  A non-positive pivot does not change the control flow: the factorisation runs on
+// with NaNs, the diagonal warp raises a flag and the owner of S marks the point singular.
 #include <type_traits>
 #include "ked_common.cuh"
 

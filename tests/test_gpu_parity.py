@@ -153,6 +153,34 @@ def test_krig_overrides_and_single_month(env):
         assert abs(om - mean[i, 0]) < TOL_C and abs(ov - var[i, 0]) <= TOL_VAR_REL * abs(ov)
 
 
+def test_krig_every_size_class_vs_oracle(env):
+    """Neighbour counts from the smallest system to the reference's maximum (147 = size class NB 19), with and without
+    padding of the last tile row (n a multiple of 8): each count exercises another launch of the kriging stage."""
+    lat, lon, elev, tdi, lst, _ = _pts(env, 3, 11)
+    ctx, oda = env["ctx"][0], env["oda"][0]
+    ss = o.StationSelect(oda, ctx.mask)
+    kt = o.KrigTair(ss)
+    pt = o.build_empty_pt()
+    for n in (6, 8, 9, 16, 35, 40, 64, 71, 80, 88, 96, 100, 104, 128, 147):
+        mean, var, st = ctx.krig(lat, lon, elev, lst[0], mth=5, nnghs=n, vario=(0.2, 1.1, 120.0))
+        assert np.all(st == 0), n
+        for i in range(lat.size):
+            pt[o.LAT], pt[o.LON], pt[o.ELEV] = lat[i], lon[i], elev[i]
+            pt[o.lst_name(5)] = lst[0][i, 4]
+            om, ov = kt.krig(pt, 5, nnghs=n, vario_params=(0.2, 1.1, 120.0))
+            assert abs(om - mean[i, 0]) < TOL_C, (n, i, om, mean[i, 0])
+            assert abs(ov - var[i, 0]) <= TOL_VAR_REL * abs(ov), (n, i, ov, var[i, 0])
+
+
+def test_empty_batch_is_a_no_op(env):
+    ctx = env["ctx"][0]
+    z = np.zeros(0)
+    mean, var, st = ctx.krig(z, z, z, np.zeros((0, 12)), mth=0)
+    assert mean.shape[0] == 0 and var.shape[0] == 0 and st.shape[0] == 0
+    idx, dist, wgt, st = ctx.knn(z, z, 35)
+    assert idx.shape[0] == 0 and st.shape[0] == 0
+
+
 def test_krig_colocated_stations_are_singular():
     """Two stations at the same location make the kriging covariance matrix singular: gstat stops, the drivers leave
     the fill value (step25:154-160).  The library decides it exactly (a zero station-station distance inside the
@@ -327,10 +355,11 @@ def test_krig_right_looking_kernel_in_fresh_process():
     """The experimental register-resident kriging kernel (csrc/ked_rl.cu, TWXI_KED_RL=1) against the same oracle
     checks.  The kernel choice is read once, when the library initialises its kriging stage, so the checks run in a
     fresh interpreter."""
-    sel = "test_krig_vs_oracle or test_krig_overrides_and_single_month or test_krig_colocated or test_interp_chunk_vs_oracle"
+    sel = ("test_krig_vs_oracle or test_krig_overrides_and_single_month or test_krig_colocated or "
+           "test_krig_every_size_class or test_interp_chunk_vs_oracle")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k", sel,
                         "-p", "no:cacheprovider"], env=dict(os.environ, TWXI_KED_RL="1"),
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:]
-    assert "4 passed" in r.stdout, r.stdout[-500:]
+    assert "5 passed" in r.stdout, r.stdout[-500:]

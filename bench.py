@@ -116,6 +116,25 @@ def _cpu_model():
     return "unknown"
 
 
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """Rank 0 prints exactly ONE line on stdout.  Libraries write there too (NCCL announces its version on fd 1 when the
+    first communicator is created), so fd 1 is pointed at stderr for the rest of the process and the JSON line goes to a
+    private duplicate of the original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path (oracle port; the real one needs
     Python 2 + R/gstat + mpi4py) on all host cores, each step a bounded sample of the same workload."""
@@ -143,7 +162,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": base,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    _emit(line)
 
 
 def main():
@@ -158,6 +177,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    _claim_stdout()
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -314,7 +334,7 @@ def main():
             "wall_s_timed_region": t_wall}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(da, wrk, args.cpu_cells)
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -215,6 +215,20 @@ int twxi_interp_chunk(twxi_ctx* ctx_tmin, twxi_ctx* ctx_tmax, const double* wrk_
                       float* tmin_se, float* tmax_se, int32_t* ninvalid, uint8_t* status, int mem);
 
 /*
+ * The same call without the final wait, for drivers that work through a list of chunks the way the step25 worker
+ * loop does (results go to a writer, step25:176-196, while the next chunk is computed).  With host buffers the results
+ * leave the device on a copy stream from double-buffered staging, so the device -> host copy of one chunk overlaps the
+ * kernels of the next; the caller's buffers (wrk_chk included, which must be pinned for the overlap to happen) belong
+ * to the library until twxi_interp_chunk_wait(ctx_tmin, 1) returns or two further chunks have been submitted.
+ * twxi_interp_chunk_wait(ctx_tmin, 0) only orders ctx_tmin's stream after the last copy (for event timing);
+ * with host_sync != 0 it also blocks until everything submitted so far is complete.  One submitting thread per context pair.
+ */
+int twxi_interp_chunk_async(twxi_ctx* ctx_tmin, twxi_ctx* ctx_tmax, const double* wrk_chk, int ny, int nx,
+                            int16_t* tmin, int16_t* tmax, float* tmin_norm, float* tmax_norm,
+                            float* tmin_se, float* tmax_se, int32_t* ninvalid, uint8_t* status, int mem);
+int twxi_interp_chunk_wait(twxi_ctx* ctx_tmin, int host_sync);
+
+/*
  * Instrumentation for bench.py: number of kernels this library launched on the calling thread's contexts
  * since the last reset, and per-stage device time (ms) of the most recent twxi_interp_chunk /
  * twxi_interp_cells / twxi_interp_points call when timing was enabled (stage order: knn, nngh_params, krig,

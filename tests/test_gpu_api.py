@@ -260,3 +260,35 @@ def test_xval_tair_anom_class(env):
         assert np.abs(r2[i] - rr).max() < 1e-8
     b1, m1, r1 = xv_gpu.run_xval(ids[0], a_nnghs)                  # reference signature
     assert np.array_equal(b1, bias[0]) and np.array_equal(m1, mae[0]) and np.array_equal(r1, r2[0])
+
+
+def test_async_chunks_equal_synchronous_calls(env):
+    """twxi_interp_chunk_async: three chunks submitted back to back from pinned host buffers (staging slots are reused
+    from the third on), results byte-identical to the synchronous call."""
+    import torch
+    from topowx_b200.context import TwxiContext, interp_chunk, interp_chunk_wait
+    synth, f, db = env["synth"], env["f"], env["db"]
+    ctx = [TwxiContext(d, np.isnan(d.stns[db.BAD])) for d in env["da"]]
+    chunks = [synth.make_wrk_chk(f, synth.TILE_ROW0 + r, synth.TILE_COL0 + c, 6, 7) for r, c in ((3, 5), (120, 40), (200, 210))]
+    chunks[1][2, 2:4, 1:3] = 0                                   # some masked cells
+    ref = [interp_chunk(ctx[0], ctx[1], w) for w in chunks]
+    nd = ctx[0].ndays
+
+    def pinned():
+        mk = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+        return dict(tmin=mk((nd, 6, 7), torch.int16), tmax=mk((nd, 6, 7), torch.int16),
+                    tmin_norm=mk((12, 6, 7), torch.float32), tmax_norm=mk((12, 6, 7), torch.float32),
+                    tmin_se=mk((12, 6, 7), torch.float32), tmax_se=mk((12, 6, 7), torch.float32),
+                    ninvalid=mk((6, 7), torch.int32), status=mk((6, 7), torch.uint8))
+    outs = [pinned() for _ in chunks]
+    wrks = [torch.from_numpy(w).pin_memory() for w in chunks]
+    for w, out in zip(wrks, outs):
+        interp_chunk(ctx[0], ctx[1], w, out=out, wait=False)
+    interp_chunk_wait(ctx[0])
+    for r, out in zip(ref, outs):
+        for k in r:
+            np.testing.assert_array_equal(np.asarray(r[k]), out[k].numpy(), err_msg=k)
+    # and the synchronous call still works afterwards
+    again = interp_chunk(ctx[0], ctx[1], chunks[0])
+    for k in again:
+        np.testing.assert_array_equal(np.asarray(ref[0][k]), np.asarray(again[k]), err_msg=k)

@@ -66,6 +66,8 @@ def _load():
         "twxi_interp_points": (i32, [vp, C.POINTER(Points), vp, vp, vp, vp, vp, i32]),
         "twxi_interp_cells": (i32, [vp, vp, i32] + [vp] * 8 + [i32, i32, i32] + [vp] * 8 + [i32]),
         "twxi_interp_chunk": (i32, [vp, vp, vp, i32, i32] + [vp] * 8 + [i32]),
+        "twxi_interp_chunk_async": (i32, [vp, vp, vp, i32, i32] + [vp] * 8 + [i32]),
+        "twxi_interp_chunk_wait": (i32, [vp, i32]),
         "twxi_measure_fp64_peak": (i32, [i32, vp, vp]),
     }
     for name, (res, args) in sig.items():

@@ -187,9 +187,11 @@ def interp_cells(ctx_tmin, ctx_tmax, lat, lon, elev, tdi, climdiv, lst_tmin, lst
     return tmin, tmax, o[0], o[1], o[2], o[3], ninv, st
 
 
-def interp_chunk(ctx_tmin, ctx_tmax, wrk_chk, out=None, daily=True):
+def interp_chunk(ctx_tmin, ctx_tmax, wrk_chk, out=None, daily=True, wait=True):
     """twxi_interp_chunk on a work chunk ``f8[32, ny, nx]`` (numpy / pinned torch host tensor / CUDA tensor).
-    ``out`` may carry preallocated result buffers (same memory space as ``wrk_chk``)."""
+    ``out`` may carry preallocated result buffers (same memory space as ``wrk_chk``).  ``wait=False`` submits the chunk
+    with twxi_interp_chunk_async: the results are valid after ``interp_chunk_wait`` (or two further submissions) and the
+    copy to the host overlaps the next chunk's kernels."""
     dev = _lib.is_device(wrk_chk)
     _, ny, nx = wrk_chk.shape
     nd = ctx_tmin.ndays
@@ -208,8 +210,14 @@ def interp_chunk(ctx_tmin, ctx_tmax, wrk_chk, out=None, daily=True):
                        tmin_norm=np.empty((12, ny, nx), np.float32), tmax_norm=np.empty((12, ny, nx), np.float32),
                        tmin_se=np.empty((12, ny, nx), np.float32), tmax_se=np.empty((12, ny, nx), np.float32),
                        ninvalid=np.empty((ny, nx), np.int32), status=np.empty((ny, nx), np.uint8))
-    check(lib.twxi_interp_chunk(ctx_tmin.handle, ctx_tmax.handle, ptr(wrk_chk), int(ny), int(nx),
-                                ptr(out["tmin"]), ptr(out["tmax"]), ptr(out["tmin_norm"]), ptr(out["tmax_norm"]),
-                                ptr(out["tmin_se"]), ptr(out["tmax_se"]), ptr(out["ninvalid"]), ptr(out["status"]),
-                                MEM_DEVICE if dev else MEM_HOST))
+    fn = lib.twxi_interp_chunk if wait else lib.twxi_interp_chunk_async
+    check(fn(ctx_tmin.handle, ctx_tmax.handle, ptr(wrk_chk), int(ny), int(nx),
+             ptr(out["tmin"]), ptr(out["tmax"]), ptr(out["tmin_norm"]), ptr(out["tmax_norm"]),
+             ptr(out["tmin_se"]), ptr(out["tmax_se"]), ptr(out["ninvalid"]), ptr(out["status"]),
+             MEM_DEVICE if dev else MEM_HOST))
     return out
+
+
+def interp_chunk_wait(ctx_tmin, host_sync=True):
+    """Completion of the chunks submitted with ``interp_chunk(..., wait=False)`` (twxi_interp_chunk_wait)."""
+    check(lib.twxi_interp_chunk_wait(ctx_tmin.handle, 1 if host_sync else 0))

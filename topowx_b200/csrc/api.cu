@@ -188,6 +188,42 @@ struct Scratch {
 };
 static thread_local Scratch g_scratch[4];
 
+// State of the asynchronous work-chunk call (twxi_interp_chunk_async): results leave the device on a copy stream from
+// double-buffered staging, so that the device -> host copy of chunk t overlaps the kernels of chunk t+1.
+struct AsyncOut {
+    cudaStream_t copy = nullptr;
+    cudaEvent_t done = nullptr;           // compute stream: staging of the current call written
+    cudaEvent_t copied[2] = {nullptr, nullptr};   // copy stream: staging slot drained to the caller's buffers
+    bool pending[2] = {false, false};
+    Scratch stage[2];
+    // the way in: work chunks go host -> device on their own stream into double-buffered staging, ahead of the kernels
+    cudaStream_t h2d = nullptr;
+    cudaEvent_t loaded[2] = {nullptr, nullptr};   // h2d stream: chunk staged
+    cudaEvent_t unpacked[2] = {nullptr, nullptr}; // compute stream: staged chunk consumed by unpack_chunk_kernel
+    bool consumed[2] = {false, false};
+    Scratch win[2];
+    int slot = 0, last = -1;
+    int init() {
+        if (copy) return TWXI_OK;
+        TWXI_CUDA(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+        TWXI_CUDA(cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking));
+        TWXI_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) {
+            TWXI_CUDA(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
+            TWXI_CUDA(cudaEventCreateWithFlags(&loaded[i], cudaEventDisableTiming));
+            TWXI_CUDA(cudaEventCreateWithFlags(&unpacked[i], cudaEventDisableTiming));
+        }
+        return TWXI_OK;
+    }
+};
+static thread_local AsyncOut g_async;
+
+template <typename T>
+static int copy_out_on(cudaStream_t s, T* dst, const T* src, size_t count) {
+    if (dst && count) TWXI_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyDefault, s));
+    return TWXI_OK;
+}
+
 static bool is_device_ptr(const void* p) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -666,9 +702,9 @@ int twxi_interp_cells(twxi_ctx* cmin, twxi_ctx* cmax, int ncells, const double* 
     return rc;
 }
 
-int twxi_interp_chunk(twxi_ctx* cmin, twxi_ctx* cmax, const double* wrk_chk, int ny, int nx, int16_t* tmin,
-                      int16_t* tmax, float* tmin_norm, float* tmax_norm, float* tmin_se, float* tmax_se,
-                      int32_t* ninvalid, uint8_t* status, int mem) {
+static int interp_chunk_impl(twxi_ctx* cmin, twxi_ctx* cmax, const double* wrk_chk, int ny, int nx, int16_t* tmin,
+                             int16_t* tmax, float* tmin_norm, float* tmax_norm, float* tmin_se, float* tmax_se,
+                             int32_t* ninvalid, uint8_t* status, int mem, bool async) {
     TWXI_ARG(wrk_chk && tmin_norm && tmax_norm && tmin_se && tmax_se && ninvalid && status, "null argument");
     TWXI_ARG((tmin == nullptr) == (tmax == nullptr), "tmin and tmax must both be given or both be null");
     TWXI_ARG(ny >= 1 && nx >= 1 && (long long)ny * nx <= (1 << 24), "bad chunk size");
@@ -691,7 +727,21 @@ int twxi_interp_chunk(twxi_ctx* cmin, twxi_ctx* cmax, const double* wrk_chk, int
         // device staging of the chunk and of the results when the caller's buffers are on the host
         const size_t wrk_bytes = (size_t)32 * ncell * 8;
         const double* d_wrk = wrk_chk;
-        if (host) {
+        const bool acopy = async && host;                    // chunk and results travel on the copy streams
+        AsyncOut& ao = g_async;
+        if (acopy && (rc = ao.init()) != TWXI_OK) break;
+        if (acopy) {
+            double* w;
+            const int sl = ao.slot;
+            if ((rc = ao.win[sl].get((void**)&w, wrk_bytes)) != TWXI_OK) break;
+            bool ok = true;
+            if (ao.consumed[sl]) ok = cudaStreamWaitEvent(ao.h2d, ao.unpacked[sl], 0) == cudaSuccess;    // slot free again
+            ok = ok && cudaMemcpyAsync(w, wrk_chk, wrk_bytes, cudaMemcpyHostToDevice, ao.h2d) == cudaSuccess;
+            ok = ok && cudaEventRecord(ao.loaded[sl], ao.h2d) == cudaSuccess;
+            ok = ok && cudaStreamWaitEvent(cmin->stream, ao.loaded[sl], 0) == cudaSuccess;
+            if (!ok) { set_error("wrk_chk copy failed"); rc = TWXI_ERR_CUDA; break; }
+            d_wrk = w;
+        } else if (host) {
             double* w;
             if ((rc = g_scratch[2].get((void**)&w, wrk_bytes)) != TWXI_OK) break;
             if (cudaMemcpyAsync(w, wrk_chk, wrk_bytes, cudaMemcpyHostToDevice, cmin->stream) != cudaSuccess) {
@@ -706,7 +756,8 @@ int twxi_interp_chunk(twxi_ctx* cmin, twxi_ctx* cmax, const double* wrk_chk, int
         uint8_t* d_st = status;
         if (host) {
             char* o;
-            if ((rc = g_scratch[0].get((void**)&o, 2 * q_bytes + 4 * f_bytes + (size_t)ncell * 5 + 64)) != TWXI_OK) break;
+            Scratch& so = acopy ? ao.stage[ao.slot] : g_scratch[0];
+            if ((rc = so.get((void**)&o, 2 * q_bytes + 4 * f_bytes + (size_t)ncell * 5 + 64)) != TWXI_OK) break;
             d_fnmin = reinterpret_cast<float*>(o); d_fnmax = d_fnmin + (size_t)12 * ncell;
             d_fsemin = d_fnmax + (size_t)12 * ncell; d_fsemax = d_fsemin + (size_t)12 * ncell;
             d_ninv = reinterpret_cast<int32_t*>(d_fsemax + (size_t)12 * ncell);
@@ -718,14 +769,38 @@ int twxi_interp_chunk(twxi_ctx* cmin, twxi_ctx* cmax, const double* wrk_chk, int
         ta.begin(cmin->stream);
         if ((rc = launch_unpack_chunk(cmin->stream, d_wrk, ny, nx, cmin->climdivs, cmin->n_climdivs, cmax->climdivs,
                                       cmax->n_climdivs, cmin->b, cmax->b)) != TWXI_OK) break;
+        if (acopy) {
+            if (cudaEventRecord(ao.unpacked[ao.slot], cmin->stream) != cudaSuccess) { set_error("event record failed"); rc = TWXI_ERR_CUDA; break; }
+            ao.consumed[ao.slot] = true;
+        }
         if ((rc = run_variable(*cmin, daily, &ta)) != TWXI_OK) break;
         ta.mark(5);
         tb.begin(cmin->stream);
         if ((rc = run_variable(*cmax, daily, &tb)) != TWXI_OK) break;
+        if (acopy && ao.pending[ao.slot]) {                  // the staging slot is still being drained (two calls ago)
+            if (cudaStreamWaitEvent(cmin->stream, ao.copied[ao.slot], 0) != cudaSuccess) { set_error("event wait failed"); rc = TWXI_ERR_CUDA; break; }
+        }
         if ((rc = launch_fixer(*cmin, *cmax, ncell, 1, daily ? 1 : 0, d_st, nullptr, nullptr, nullptr, nullptr, d_qmin,
                                d_qmax, d_fnmin, d_fnmax, d_fsemin, d_fsemax, d_ninv)) != TWXI_OK) break;
         tb.mark(5);
-        if (host) {
+        if (acopy) {
+            cudaStream_t cs = ao.copy;
+            if (cudaEventRecord(ao.done, cmin->stream) != cudaSuccess || cudaStreamWaitEvent(cs, ao.done, 0) != cudaSuccess) {
+                set_error("event record failed"); rc = TWXI_ERR_CUDA; break;
+            }
+            if ((rc = copy_out_on(cs, tmin, d_qmin, (size_t)nd * ncell)) != TWXI_OK) break;
+            if ((rc = copy_out_on(cs, tmax, d_qmax, (size_t)nd * ncell)) != TWXI_OK) break;
+            if ((rc = copy_out_on(cs, tmin_norm, d_fnmin, (size_t)12 * ncell)) != TWXI_OK) break;
+            if ((rc = copy_out_on(cs, tmax_norm, d_fnmax, (size_t)12 * ncell)) != TWXI_OK) break;
+            if ((rc = copy_out_on(cs, tmin_se, d_fsemin, (size_t)12 * ncell)) != TWXI_OK) break;
+            if ((rc = copy_out_on(cs, tmax_se, d_fsemax, (size_t)12 * ncell)) != TWXI_OK) break;
+            if ((rc = copy_out_on(cs, ninvalid, d_ninv, (size_t)ncell)) != TWXI_OK) break;
+            if ((rc = copy_out_on(cs, status, d_st, (size_t)ncell)) != TWXI_OK) break;
+            if (cudaEventRecord(ao.copied[ao.slot], cs) != cudaSuccess) { set_error("event record failed"); rc = TWXI_ERR_CUDA; break; }
+            ao.pending[ao.slot] = true;
+            ao.last = ao.slot;
+            ao.slot ^= 1;
+        } else if (host) {
             if ((rc = copy_out(*cmin, tmin, d_qmin, (size_t)nd * ncell)) != TWXI_OK) break;
             if ((rc = copy_out(*cmin, tmax, d_qmax, (size_t)nd * ncell)) != TWXI_OK) break;
             if ((rc = copy_out(*cmin, tmin_norm, d_fnmin, (size_t)12 * ncell)) != TWXI_OK) break;
@@ -737,10 +812,38 @@ int twxi_interp_chunk(twxi_ctx* cmin, twxi_ctx* cmax, const double* wrk_chk, int
         }
         ta.end(false);
         tb.end(true);
-        rc = finish(*cmin, mem);
+        if (!async) rc = finish(*cmin, mem);
     } while (0);
     cmax->stream = saved;
     return rc;
+}
+
+int twxi_interp_chunk(twxi_ctx* cmin, twxi_ctx* cmax, const double* wrk_chk, int ny, int nx, int16_t* tmin,
+                      int16_t* tmax, float* tmin_norm, float* tmax_norm, float* tmin_se, float* tmax_se,
+                      int32_t* ninvalid, uint8_t* status, int mem) {
+    return interp_chunk_impl(cmin, cmax, wrk_chk, ny, nx, tmin, tmax, tmin_norm, tmax_norm, tmin_se, tmax_se, ninvalid,
+                             status, mem, false);
+}
+
+int twxi_interp_chunk_async(twxi_ctx* cmin, twxi_ctx* cmax, const double* wrk_chk, int ny, int nx, int16_t* tmin,
+                            int16_t* tmax, float* tmin_norm, float* tmax_norm, float* tmin_se, float* tmax_se,
+                            int32_t* ninvalid, uint8_t* status, int mem) {
+    return interp_chunk_impl(cmin, cmax, wrk_chk, ny, nx, tmin, tmax, tmin_norm, tmax_norm, tmin_se, tmax_se, ninvalid,
+                             status, mem, true);
+}
+
+int twxi_interp_chunk_wait(twxi_ctx* cmin, int host_sync) {
+    TWXI_ARG(cmin != nullptr, "null context");
+    TWXI_CUDA(cudaSetDevice(cmin->device));
+    AsyncOut& ao = g_async;
+    if (ao.last >= 0) TWXI_CUDA(cudaStreamWaitEvent(cmin->stream, ao.copied[ao.last], 0));    // stream order: after the last copy
+    if (host_sync) {
+        TWXI_CUDA(cudaStreamSynchronize(cmin->stream));
+        ao.pending[0] = ao.pending[1] = false;
+        ao.consumed[0] = ao.consumed[1] = false;
+        ao.last = -1;
+    }
+    return TWXI_OK;
 }
 
 }  // extern "C"

@@ -197,13 +197,20 @@ class PtInterpTair(object):
             a_pt[get_norm_varname(m)] = nmax[0, m - 1]
         return tmin[0], tmax[0], nmin[0], nmax[0], semin[0], semax[0], int(ninv[0]) if fix_invalid else 0
 
-    def interp_chunk(self, wrk_chk, out=None):
+    def interp_chunk(self, wrk_chk, out=None, wait=True):
         '''
         Batch form (new): one work chunk f8[32, ny, nx] exactly as Tiler.next() builds it (tiling.py:205-213);
         replaces the per-cell loop of step25_mpi_interp_tair.py:126-175.  Returns the step25 result buffers
         (tmin/tmax int16 [ndays, ny, nx], *_norm/*_se float32 [12, ny, nx], ninvalid int32, status uint8).
+        wait=False submits the chunk and returns at once (pinned wrk_chk / out buffers; the results are valid after
+        interp_chunk_wait), the way the worker loop hands a chunk to the writer while it computes the next
+        (step25:176-196).
         '''
-        return _context.interp_chunk(self.ctx_tmin, self.ctx_tmax, wrk_chk, out=out, daily=not self.norms_only)
+        return _context.interp_chunk(self.ctx_tmin, self.ctx_tmax, wrk_chk, out=out, daily=not self.norms_only, wait=wait)
+
+    def interp_chunk_wait(self):
+        '''Completion of the chunks submitted with interp_chunk(..., wait=False).'''
+        _context.interp_chunk_wait(self.ctx_tmin)
 
 
 class StationDataWrkChk(StationSerialDataDb):

@@ -202,9 +202,13 @@ struct AsyncOut {
     cudaEvent_t unpacked[2] = {nullptr, nullptr}; // compute stream: staged chunk consumed by unpack_chunk_kernel
     bool consumed[2] = {false, false};
     Scratch win[2];
-    int slot = 0, last = -1;
-    int init() {
-        if (copy) return TWXI_OK;
+    int slot = 0, last = -1, device = -1;
+    int init(int dev) {
+        if (copy) {
+            if (dev != device) { set_error("asynchronous chunks: one device per submitting thread"); return TWXI_ERR_ARG; }
+            return TWXI_OK;
+        }
+        device = dev;
         TWXI_CUDA(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
         TWXI_CUDA(cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking));
         TWXI_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
@@ -729,7 +733,7 @@ static int interp_chunk_impl(twxi_ctx* cmin, twxi_ctx* cmax, const double* wrk_c
         const double* d_wrk = wrk_chk;
         const bool acopy = async && host;                    // chunk and results travel on the copy streams
         AsyncOut& ao = g_async;
-        if (acopy && (rc = ao.init()) != TWXI_OK) break;
+        if (acopy && (rc = ao.init(cmin->device)) != TWXI_OK) break;
         if (acopy) {
             double* w;
             const int sl = ao.slot;

@@ -1,4 +1,6 @@
 """Host-side logic that needs no GPU: synthetic inputs, the station-DB container, Tiler / partitioning."""
+import os
+
 import numpy as np
 import pytest
 
@@ -117,3 +119,22 @@ def test_build_nstn_bandwidths_matches_reference_set():
     from topowx_b200.interp import build_nstn_bandwidths
     assert build_nstn_bandwidths(35, 150, 0.10).tolist() == [35, 39, 43, 47, 52, 57, 63, 69, 76, 84, 92, 101, 111, 122,
                                                              134, 147]
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference (the oracle port on the host cores): exactly one line on stdout, carrying the keys of the
+    bench contract; anything a library prints on fd 1 must not end up in front of it."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       env=dict(os.environ, TWX_REF_CELLS_PER_STEP="4"), cwd=root, stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-1000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "cell-days/s" and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["value"] > 0

@@ -14,7 +14,9 @@
  *  - `mem` says where the caller's query / result buffers live: TWXI_MEM_HOST or TWXI_MEM_DEVICE.
  *    Context creation and twxi_ctx_set_obs always take host pointers.
  *  - Calls on one context are serialised on its stream (twxi_ctx_set_stream, default: the legacy default
- *    stream).  With TWXI_MEM_HOST the call returns after results are in the host buffers; with
+ *    stream).  Every device workspace (query batch, candidate lists, kriging scratch, staging) belongs to the
+ *    context, so different contexts may be driven on different streams / devices, from one host thread or several;
+ *    one context must not be used from two threads at once.  With TWXI_MEM_HOST the call returns after results are in the host buffers; with
  *    TWXI_MEM_DEVICE it returns after enqueueing (results are stream-ordered).
  *  - Return value: TWXI_OK or a negative error for API misuse / CUDA failures (twxi_last_error() has text).
  *    Per-point failures never fail the call: they are reported in a per-point status byte and the point's
@@ -53,6 +55,7 @@ extern "C" {
 #define TWXI_ST_FIXER_EMPTY 5   /* 'No valid tmin/tmax in window'                          interp_tair.py:192     */
 #define TWXI_ST_CLIMDIV 6       /* KeyError: climate division unknown to the station DB    interp_tair.py:563     */
 #define TWXI_ST_KNN_TIES 7      /* more than 512 exact distance ties at the selection boundary (unsupported)     */
+#define TWXI_ST_LIMIT 8         /* neighbour count of the point exceeds TWXI_MAX_KRIG_NNGHS (kriging kernel limit) */
 #define TWXI_ST_MASKED 255      /* chunk cell with mask == 0: not a failure, nothing computed (step25:132)      */
 
 /* fill values of the result buffers = netCDF4.default_fillvals (step25:71-88) */
@@ -65,6 +68,7 @@ extern "C" {
 #define TWXI_INIT_NNGHS 100
 /* limits of this build */
 #define TWXI_MAX_NNGHS 255      /* largest neighbour count (k+1 candidates are kept per point)  */
+#define TWXI_MAX_KRIG_NNGHS 168 /* largest kriging neighbour count (k_norm); larger -> TWXI_ST_LIMIT per point */
 #define TWXI_MAX_STNS 24000     /* stations per context (kNN key table lives in shared memory)  */
 #define TWXI_MAX_RM 4           /* leave-out station indices per point                          */
 
@@ -191,13 +195,16 @@ int twxi_interp_points(twxi_ctx* ctx, const twxi_points* pts, double* daily, dou
  * a11 / a12: Tmin and Tmax at ncells points with the Tmin>=Tmax fixer.  Replaces PtInterpTair.interp_pt
  * (interp_tair.py:526-592) incl. tmin_tmax_fixer (:143-197) and the 1981-2010 normals recomputation
  * (:583-590).  lst_tmin / lst_tmax [ncells][12] are the "tminMM"/"tmaxMM" LST planes; climdiv may be NULL
- * (no check).  Outputs float64: tmin, tmax [ncells][ndays]; norms/se [ncells][12] each; ninvalid int32;
- * status uint8.
+ * (no check).  rm_idx_tmin / rm_idx_tmax int32 [ncells][n_rm] are the stns_rm leave-outs as indices into the
+ * station table of the RESPECTIVE context (-1 = none; the two tables are different subsets of the DB, so one station
+ * id maps to two different indices, interp_tair.py:565,574); both NULL when n_rm == 0.
+ * Outputs float64: tmin, tmax [ncells][ndays]; norms/se [ncells][12] each; ninvalid int32; status uint8.
  */
 int twxi_interp_cells(twxi_ctx* ctx_tmin, twxi_ctx* ctx_tmax, int ncells,
                       const double* lat, const double* lon, const double* elev, const double* tdi,
                       const double* climdiv, const double* lst_tmin, const double* lst_tmax,
-                      const int32_t* rm_idx, int n_rm, int rm_zero_dist, int fix_invalid,
+                      const int32_t* rm_idx_tmin, const int32_t* rm_idx_tmax, int n_rm, int rm_zero_dist,
+                      int fix_invalid,
                       double* tmin, double* tmax, double* tmin_norms, double* tmax_norms,
                       double* tmin_se, double* tmax_se, int32_t* ninvalid, uint8_t* status, int mem);
 
@@ -219,9 +226,13 @@ int twxi_interp_chunk(twxi_ctx* ctx_tmin, twxi_ctx* ctx_tmax, const double* wrk_
  * loop does (results go to a writer, step25:176-196, while the next chunk is computed).  With host buffers the results
  * leave the device on a copy stream from double-buffered staging, so the device -> host copy of one chunk overlaps the
  * kernels of the next; the caller's buffers (wrk_chk included, which must be pinned for the overlap to happen) belong
- * to the library until twxi_interp_chunk_wait(ctx_tmin, 1) returns or two further chunks have been submitted.
- * twxi_interp_chunk_wait(ctx_tmin, 0) only orders ctx_tmin's stream after the last copy (for event timing);
- * with host_sync != 0 it also blocks until everything submitted so far is complete.  One submitting thread per context pair.
+ * to the library until twxi_interp_chunk_wait(ctx_tmin, 1) returns, or until TWO further chunks have been submitted on the
+ * same context pair: the submission of chunk t+2 blocks the calling host thread until chunk t's work chunk has been read
+ * and chunk t's results are complete in the caller's host buffers (it reuses chunk t's staging slot), so a driver may
+ * cycle through three sets of pinned buffers without ever calling the wait.  Submitting chunk t+1 guarantees nothing
+ * about chunk t.  twxi_interp_chunk_wait(ctx_tmin, 0) only orders ctx_tmin's stream after the last copy (for event
+ * timing); with host_sync != 0 it also blocks until everything submitted so far is complete.  The staging, the copy
+ * streams and the events belong to ctx_tmin; one submitting thread per context pair.
  */
 int twxi_interp_chunk_async(twxi_ctx* ctx_tmin, twxi_ctx* ctx_tmax, const double* wrk_chk, int ny, int nx,
                             int16_t* tmin, int16_t* tmax, float* tmin_norm, float* tmax_norm,

@@ -349,17 +349,3 @@ def test_conus_scale_station_table():
             continue
         assert st[i] == 0
         assert np.abs(on - norms[i]).max() < TOL_C and np.abs(od - dly[i]).max() < TOL_C
-
-
-def test_krig_right_looking_kernel_in_fresh_process():
-    """The experimental register-resident kriging kernel (csrc/ked_rl.cu, TWXI_KED_RL=1) against the same oracle
-    checks.  The kernel choice is read once, when the library initialises its kriging stage, so the checks run in a
-    fresh interpreter."""
-    sel = ("test_krig_vs_oracle or test_krig_overrides_and_single_month or test_krig_colocated or "
-           "test_krig_every_size_class or test_interp_chunk_vs_oracle")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k", sel,
-                        "-p", "no:cacheprovider"], env=dict(os.environ, TWXI_KED_RL="1"),
-                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
-                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-2000:]
-    assert "5 passed" in r.stdout, r.stdout[-500:]

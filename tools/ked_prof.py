@@ -18,10 +18,9 @@ lib.twxi_ked_prof(buf, 1)
 v = np.array(list(buf), dtype=np.float64)
 n = max(v[0], 1)
 print("problems", int(v[0]))
-for i, nm in ((1, "prologue total"), (2, "  B' build + TMA issue"), (3, "  covariance pass"), (13, "  wait for the distance tiles (mbarrier)"),
-              (14, "  barrier: previous problem consumed"), (15, "  barrier: prologue done"), (4, "diag: stage loop total"),
+for i, nm in ((1, "top of problem -> inputs landed"), (4, "diag: stage loop total"),
               (5, "  barrier wait"), (6, "  chol8_inverse"), (7, "  post-barrier DMMA part")):
     print("   %-28s %9.0f cycles" % (nm, v[i] / n))
 n = max(v[8], 1)
-for i, nm in ((9, "worker0: stage loop total"), (10, "  barrier wait"), (11, "  lk1 + phase A"), (12, "  phase B")):
+for i, nm in ((9, "worker0: stage loop total"), (10, "  barrier wait"), (11, "  stage_rows"), (12, "  wait for L(K+1,K)")):
     print("   %-28s %9.0f cycles" % (nm, v[i] / n))

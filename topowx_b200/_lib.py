@@ -9,12 +9,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TWXI_LIB") or os.path.join(HERE, "libtwxi.so")   # TWXI_LIB: instrumented developer builds
 
 MEM_HOST, MEM_DEVICE = 0, 1
-ST_OK, ST_NO_NNGHS, ST_NO_VARIO, ST_TOO_FEW_STNS, ST_SINGULAR, ST_FIXER_EMPTY, ST_CLIMDIV, ST_KNN_TIES = range(8)
+ST_OK, ST_NO_NNGHS, ST_NO_VARIO, ST_TOO_FEW_STNS, ST_SINGULAR, ST_FIXER_EMPTY, ST_CLIMDIV, ST_KNN_TIES, ST_LIMIT = range(9)
 ST_MASKED = 255
 FILL_I2, FILL_I4 = -32767, -2147483647
 FILL_F4 = np.float32(9.969209968386869e+36)
 FILL_F8 = 9.969209968386869e+36
-INIT_NNGHS, MAX_NNGHS, MAX_STNS, MAX_RM = 100, 255, 24000, 4
+INIT_NNGHS, MAX_NNGHS, MAX_STNS, MAX_RM, MAX_KRIG_NNGHS = 100, 255, 24000, 4, 168
 
 # messages of the reference exceptions (interp_tair.py:252,829,843,192; station_select.py:164)
 STATUS_MESSAGES = {
@@ -25,6 +25,7 @@ STATUS_MESSAGES = {
     ST_FIXER_EMPTY: "No valid tmin/tmax in window",
     ST_CLIMDIV: "climate division not found in station database",
     ST_KNN_TIES: "too many exact distance ties",
+    ST_LIMIT: "neighbour count exceeds the kriging kernel's limit (%d)" % MAX_KRIG_NNGHS,
 }
 
 
@@ -64,7 +65,7 @@ def _load():
         "twxi_gwr_hat": (i32, [vp, C.POINTER(Points), i32, vp, i32, vp, vp, vp, vp, i32]),
         "twxi_gwr_mth": (i32, [vp, C.POINTER(Points), i32, vp, vp, vp, vp, i32]),
         "twxi_interp_points": (i32, [vp, C.POINTER(Points), vp, vp, vp, vp, vp, i32]),
-        "twxi_interp_cells": (i32, [vp, vp, i32] + [vp] * 8 + [i32, i32, i32] + [vp] * 8 + [i32]),
+        "twxi_interp_cells": (i32, [vp, vp, i32] + [vp] * 9 + [i32, i32, i32] + [vp] * 8 + [i32]),
         "twxi_interp_chunk": (i32, [vp, vp, vp, i32, i32] + [vp] * 8 + [i32]),
         "twxi_interp_chunk_async": (i32, [vp, vp, vp, i32, i32] + [vp] * 8 + [i32]),
         "twxi_interp_chunk_wait": (i32, [vp, i32]),

@@ -14,6 +14,11 @@ def _f8(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+def _dtype_name(a):
+    """'float64', 'int16', ... of a numpy array or a torch tensor."""
+    return str(a.dtype).replace("torch.", "")
+
+
 class TwxiContext(object):
     """Device-resident station table of the stations selected by ``stn_mask`` (default: isnan(bad), as in
     PtInterpTair.__init__, twx/interp/interp_tair.py:481-487), in DB order, plus the observations."""
@@ -166,22 +171,34 @@ class TwxiContext(object):
         return dly, norms, se, var, st
 
 
-def interp_cells(ctx_tmin, ctx_tmax, lat, lon, elev, tdi, climdiv, lst_tmin, lst_tmax, rm_idx=None, rm_zero=False,
-                 fix_invalid=True):
+def interp_cells(ctx_tmin, ctx_tmax, lat, lon, elev, tdi, climdiv, lst_tmin, lst_tmax, rm_idx_tmin=None,
+                 rm_idx_tmax=None, rm_zero=False, fix_invalid=True):
+    """twxi_interp_cells.  ``rm_idx_tmin`` / ``rm_idx_tmax`` [ncells, n_rm] are CONTEXT-LOCAL station indices (-1 = none):
+    the Tmin and Tmax station tables are different subsets of the DB, so a station has a different index in each."""
     lat = _f8(np.atleast_1d(lat)); n = lat.size
     lon, elev, tdi = _f8(np.atleast_1d(lon)), _f8(np.atleast_1d(elev)), _f8(np.atleast_1d(tdi))
     climdiv = None if climdiv is None else _f8(np.atleast_1d(climdiv))
     lst_tmin, lst_tmax = _f8(np.asarray(lst_tmin).reshape(n, 12)), _f8(np.asarray(lst_tmax).reshape(n, 12))
     n_rm = 0
-    if rm_idx is not None:
-        rm_idx = np.ascontiguousarray(np.asarray(rm_idx, dtype=np.int32).reshape(n, -1)); n_rm = rm_idx.shape[1]
+    if rm_idx_tmin is not None or rm_idx_tmax is not None:
+        ra = None if rm_idx_tmin is None else np.asarray(rm_idx_tmin, dtype=np.int32).reshape(n, -1)
+        rb = None if rm_idx_tmax is None else np.asarray(rm_idx_tmax, dtype=np.int32).reshape(n, -1)
+        n_rm = max(0 if ra is None else ra.shape[1], 0 if rb is None else rb.shape[1])
+
+        def pad(r):
+            o = -np.ones((n, n_rm), dtype=np.int32)
+            if r is not None:
+                o[:, :r.shape[1]] = r
+            return o
+        rm_idx_tmin, rm_idx_tmax = pad(ra), pad(rb)
     nd = ctx_tmin.ndays
     tmin, tmax = np.empty((n, nd)), np.empty((n, nd))
     o = [np.empty((n, 12)) for _ in range(4)]
     ninv = np.empty(n, dtype=np.int32)
     st = np.empty(n, dtype=np.uint8)
     check(lib.twxi_interp_cells(ctx_tmin.handle, ctx_tmax.handle, n, ptr(lat), ptr(lon), ptr(elev), ptr(tdi),
-                                ptr(climdiv), ptr(lst_tmin), ptr(lst_tmax), ptr(rm_idx), n_rm, int(bool(rm_zero)),
+                                ptr(climdiv), ptr(lst_tmin), ptr(lst_tmax), ptr(rm_idx_tmin), ptr(rm_idx_tmax), n_rm,
+                                int(bool(rm_zero)),
                                 int(bool(fix_invalid)), ptr(tmin), ptr(tmax), ptr(o[0]), ptr(o[1]), ptr(o[2]),
                                 ptr(o[3]), ptr(ninv), ptr(st), MEM_HOST))
     return tmin, tmax, o[0], o[1], o[2], o[3], ninv, st
@@ -189,11 +206,19 @@ def interp_cells(ctx_tmin, ctx_tmax, lat, lon, elev, tdi, climdiv, lst_tmin, lst
 
 def interp_chunk(ctx_tmin, ctx_tmax, wrk_chk, out=None, daily=True, wait=True):
     """twxi_interp_chunk on a work chunk ``f8[32, ny, nx]`` (numpy / pinned torch host tensor / CUDA tensor).
-    ``out`` may carry preallocated result buffers (same memory space as ``wrk_chk``).  ``wait=False`` submits the chunk
-    with twxi_interp_chunk_async: the results are valid after ``interp_chunk_wait`` (or two further submissions) and the
-    copy to the host overlaps the next chunk's kernels."""
+    ``out`` may carry preallocated result buffers (same memory space, dtypes and shapes are checked).  ``wait=False``
+    submits the chunk with twxi_interp_chunk_async: its buffers belong to the library until ``interp_chunk_wait`` returns or
+    until two further chunks have been submitted on the same context pair (the second submission blocks the host until this
+    chunk's results are in the host buffers); the copies overlap the neighbouring chunks' kernels."""
     dev = _lib.is_device(wrk_chk)
+    if len(wrk_chk.shape) != 3 or wrk_chk.shape[0] != 32:
+        raise ValueError("wrk_chk must be [32, ny, nx] (planes of tiling.py:205-213 / step25:273-279), got %r"
+                         % (tuple(wrk_chk.shape),))
+    if _dtype_name(wrk_chk) != "float64":
+        raise ValueError("wrk_chk must be float64, got %s" % _dtype_name(wrk_chk))
     _, ny, nx = wrk_chk.shape
+    if daily and ctx_tmin.ndays != ctx_tmax.ndays:
+        raise ValueError("tmin and tmax contexts hold observation records of different length")
     nd = ctx_tmin.ndays
     if out is None:
         if dev:
@@ -210,6 +235,20 @@ def interp_chunk(ctx_tmin, ctx_tmax, wrk_chk, out=None, daily=True, wait=True):
                        tmin_norm=np.empty((12, ny, nx), np.float32), tmax_norm=np.empty((12, ny, nx), np.float32),
                        tmin_se=np.empty((12, ny, nx), np.float32), tmax_se=np.empty((12, ny, nx), np.float32),
                        ninvalid=np.empty((ny, nx), np.int32), status=np.empty((ny, nx), np.uint8))
+    else:
+        want = dict(tmin=("int16", (nd, ny, nx)), tmax=("int16", (nd, ny, nx)), tmin_norm=("float32", (12, ny, nx)),
+                    tmax_norm=("float32", (12, ny, nx)), tmin_se=("float32", (12, ny, nx)), tmax_se=("float32", (12, ny, nx)),
+                    ninvalid=("int32", (ny, nx)), status=("uint8", (ny, nx)))
+        for k, (dt, shp) in want.items():
+            b = out.get(k)
+            if b is None:
+                if k in ("tmin", "tmax") and not daily:
+                    continue
+                raise ValueError("out[%r] is missing" % k)
+            if _dtype_name(b) != dt or tuple(b.shape) != shp:
+                raise ValueError("out[%r] must be %s %r, got %s %r" % (k, dt, shp, _dtype_name(b), tuple(b.shape)))
+            if _lib.is_device(b) != dev:
+                raise ValueError("out[%r] must live in the same memory space as wrk_chk" % k)
     fn = lib.twxi_interp_chunk if wait else lib.twxi_interp_chunk_async
     check(fn(ctx_tmin.handle, ctx_tmax.handle, ptr(wrk_chk), int(ny), int(nx),
              ptr(out["tmin"]), ptr(out["tmax"]), ptr(out["tmin_norm"]), ptr(out["tmax_norm"]),

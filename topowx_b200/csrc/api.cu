@@ -171,56 +171,31 @@ static int finish(Ctx& c, int mem) {
     return TWXI_OK;
 }
 
-// Scratch device buffers for results that need a type/layout conversion before leaving the library.
-struct Scratch {
-    void* p = nullptr;
-    size_t bytes = 0;
-    int get(void** out, size_t need) {
-        if (need > bytes) {
-            if (p) cudaFree(p);
-            p = nullptr; bytes = 0;
-            TWXI_CUDA(cudaMalloc(&p, need));
-            bytes = need;
-        }
-        *out = p;
-        return TWXI_OK;
+int AsyncOut::init() {
+    if (copy) return TWXI_OK;
+    TWXI_CUDA(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+    TWXI_CUDA(cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking));
+    TWXI_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+        TWXI_CUDA(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
+        TWXI_CUDA(cudaEventCreateWithFlags(&loaded[i], cudaEventDisableTiming));
+        TWXI_CUDA(cudaEventCreateWithFlags(&unpacked[i], cudaEventDisableTiming));
     }
-};
-static thread_local Scratch g_scratch[4];
-
-// State of the asynchronous work-chunk call (twxi_interp_chunk_async): results leave the device on a copy stream from
-// double-buffered staging, so that the device -> host copy of chunk t overlaps the kernels of chunk t+1.
-struct AsyncOut {
-    cudaStream_t copy = nullptr;
-    cudaEvent_t done = nullptr;           // compute stream: staging of the current call written
-    cudaEvent_t copied[2] = {nullptr, nullptr};   // copy stream: staging slot drained to the caller's buffers
-    bool pending[2] = {false, false};
-    Scratch stage[2];
-    // the way in: work chunks go host -> device on their own stream into double-buffered staging, ahead of the kernels
-    cudaStream_t h2d = nullptr;
-    cudaEvent_t loaded[2] = {nullptr, nullptr};   // h2d stream: chunk staged
-    cudaEvent_t unpacked[2] = {nullptr, nullptr}; // compute stream: staged chunk consumed by unpack_chunk_kernel
-    bool consumed[2] = {false, false};
-    Scratch win[2];
-    int slot = 0, last = -1, device = -1;
-    int init(int dev) {
-        if (copy) {
-            if (dev != device) { set_error("asynchronous chunks: one device per submitting thread"); return TWXI_ERR_ARG; }
-            return TWXI_OK;
-        }
-        device = dev;
-        TWXI_CUDA(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
-        TWXI_CUDA(cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking));
-        TWXI_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
-        for (int i = 0; i < 2; ++i) {
-            TWXI_CUDA(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
-            TWXI_CUDA(cudaEventCreateWithFlags(&loaded[i], cudaEventDisableTiming));
-            TWXI_CUDA(cudaEventCreateWithFlags(&unpacked[i], cudaEventDisableTiming));
-        }
-        return TWXI_OK;
+    return TWXI_OK;
+}
+void AsyncOut::destroy() {
+    for (int i = 0; i < 2; ++i) {
+        if (copied[i]) cudaEventDestroy(copied[i]);
+        if (loaded[i]) cudaEventDestroy(loaded[i]);
+        if (unpacked[i]) cudaEventDestroy(unpacked[i]);
+        stage[i].release();
+        win[i].release();
     }
-};
-static thread_local AsyncOut g_async;
+    if (done) cudaEventDestroy(done);
+    if (copy) cudaStreamDestroy(copy);
+    if (h2d) cudaStreamDestroy(h2d);
+    *this = AsyncOut();
+}
 
 template <typename T>
 static int copy_out_on(cudaStream_t s, T* dst, const T* src, size_t count) {
@@ -357,6 +332,10 @@ int twxi_ctx_destroy(twxi_ctx* c) {
     for (void* p : c->obs_owned) cudaFree(p);
     if (c->climdivs) cudaFree(c->climdivs);
     free_batch(c->b);
+    for (auto& sc : c->scratch) sc.release();
+    c->async.destroy();
+    ked_work_free(c->ked);
+    knn_work_free(c->knn);
     delete c;
     return TWXI_OK;
 }
@@ -383,6 +362,7 @@ int twxi_ctx_set_climdivs(twxi_ctx* c, const double* cd, int n) {
 
 int twxi_ctx_set_obs(twxi_ctx* c, const float* obs, int ndays, const int32_t* month, const int32_t* year) {
     TWXI_ARG(c && obs && month && year && ndays >= 1, "bad obs arguments");
+    TWXI_ARG((long long)c->n * ndays < (1LL << 31), "n_stns * ndays must stay below 2^31 (32-bit row offsets into the obs table)");
     TWXI_CUDA(cudaSetDevice(c->device));
     TWXI_CUDA(cudaStreamSynchronize(c->stream));
     for (void* p : c->obs_owned) cudaFree(p);
@@ -446,11 +426,11 @@ int twxi_knn(twxi_ctx* c, int npts, const double* lat, const double* lon, const 
     if (npts == 0) return TWXI_OK;
     Batch& b = c->b;
     double* wgt = nullptr;
-    if (out_wgt) TWXI_TRY(g_scratch[0].get((void**)&wgt, (size_t)npts * k1 * 8));
+    if (out_wgt) TWXI_TRY(c->scratch[0].get((void**)&wgt, (size_t)npts * k1 * 8));
     TWXI_TRY(launch_knn(*c, npts, b.lat, b.lon, b.n_rm ? b.rm_idx : nullptr, b.n_rm, b.rm_zero, k1, b.idx, b.dist,
                         wgt, b.status));
     uint8_t* st8;
-    TWXI_TRY(g_scratch[1].get((void**)&st8, npts));
+    TWXI_TRY(c->scratch[1].get((void**)&st8, npts));
     TWXI_TRY(launch_status_to_u8(c->stream, npts, b.status, st8));
     TWXI_TRY(copy_out(*c, out_idx, b.idx, (size_t)npts * k1));
     TWXI_TRY(copy_out(*c, out_dist, b.dist, (size_t)npts * k1));
@@ -478,7 +458,7 @@ static int upload_override(Ctx& c, const int32_t* ovr, int npts, int slot, const
     *dev = nullptr;
     if (!ovr) return TWXI_OK;
     int32_t* d;
-    TWXI_TRY(g_scratch[slot].get((void**)&d, (size_t)npts * 4));
+    TWXI_TRY(c.scratch[slot].get((void**)&d, (size_t)npts * 4));
     TWXI_CUDA(cudaMemcpyAsync(d, ovr, (size_t)npts * 4, cudaMemcpyDefault, c.stream));
     *dev = d;
     return TWXI_OK;
@@ -495,7 +475,7 @@ int twxi_nngh_params(twxi_ctx* c, const twxi_points* pts, int32_t* nnghs_norm, i
     TWXI_TRY(run_knn(*c));
     TWXI_TRY(launch_nngh_params(*c, b, nullptr, nullptr, 0, 1, 1, 1));
     uint8_t* st8;
-    TWXI_TRY(g_scratch[1].get((void**)&st8, npts));
+    TWXI_TRY(c->scratch[1].get((void**)&st8, npts));
     TWXI_TRY(launch_status_to_u8(c->stream, npts, b.status, st8));
     if (nnghs_norm) TWXI_CUDA(cudaMemcpy2DAsync(nnghs_norm, 48, b.nn, 96, 48, npts, cudaMemcpyDefault, c->stream));
     if (nnghs_anom) TWXI_CUDA(cudaMemcpy2DAsync(nnghs_anom, 48, b.nn + 12, 96, 48, npts, cudaMemcpyDefault, c->stream));
@@ -520,7 +500,7 @@ int twxi_krig(twxi_ctx* c, const twxi_points* pts, int mth, const int32_t* nnghs
     TWXI_TRY(upload_override(*c, nnghs_override, npts, 2, &d_ovr));
     double* d_vo = nullptr;
     if (vario_override) {
-        TWXI_TRY(g_scratch[3].get((void**)&d_vo, (size_t)npts * 24));
+        TWXI_TRY(c->scratch[3].get((void**)&d_vo, (size_t)npts * 24));
         TWXI_CUDA(cudaMemcpyAsync(d_vo, vario_override, (size_t)npts * 24, cudaMemcpyDefault, c->stream));
     }
     TWXI_TRY(run_knn(*c));
@@ -529,8 +509,8 @@ int twxi_krig(twxi_ctx* c, const twxi_points* pts, int mth, const int32_t* nnghs
     uint8_t* st8;
     double* tmp;
     const size_t cnt = (size_t)npts * (mth ? 1 : 12);
-    TWXI_TRY(g_scratch[1].get((void**)&st8, npts));
-    TWXI_TRY(g_scratch[0].get((void**)&tmp, cnt * 16));
+    TWXI_TRY(c->scratch[1].get((void**)&st8, npts));
+    TWXI_TRY(c->scratch[0].get((void**)&tmp, cnt * 16));
     TWXI_TRY(launch_status_to_u8(c->stream, npts, b.status, st8));
     TWXI_TRY(launch_gather_month(c->stream, npts, mth - 1, b.status, b.mean, tmp));
     TWXI_TRY(launch_gather_month(c->stream, npts, mth - 1, b.status, b.var, tmp + cnt));
@@ -551,7 +531,7 @@ int twxi_gwr_hat(twxi_ctx* c, const twxi_points* pts, int mth, const int32_t* nn
     int k1 = k1_for_override(*c, nnghs_override, npts, mem, nnghs_override == nullptr);
     TWXI_TRY(load_points(*c, pts, k1, false));
     if (npts == 0) return TWXI_OK;
-    TWXI_ARG(kmax >= k1 - 1 || nnghs_override, "kmax smaller than the largest possible neighbour count");
+    TWXI_ARG(kmax >= k1 - 1, "kmax smaller than the largest possible neighbour count");
     Batch& b = c->b;
     const int32_t* d_ovr;
     TWXI_TRY(upload_override(*c, nnghs_override, npts, 2, &d_ovr));
@@ -559,14 +539,14 @@ int twxi_gwr_hat(twxi_ctx* c, const twxi_points* pts, int mth, const int32_t* nn
     TWXI_TRY(launch_nngh_params(*c, b, nullptr, d_ovr, mth, 0, 1, 0));
     char* tmp;
     const size_t nz = (size_t)npts * kmax;
-    TWXI_TRY(g_scratch[0].get((void**)&tmp, nz * 12 + (size_t)npts * 4));
+    TWXI_TRY(c->scratch[0].get((void**)&tmp, nz * 12 + (size_t)npts * 4));
     double* d_z = reinterpret_cast<double*>(tmp);
     int32_t* d_idx = reinterpret_cast<int32_t*>(tmp + nz * 8);
     int32_t* d_k = reinterpret_cast<int32_t*>(tmp + nz * 12);
     TWXI_CUDA(cudaMemsetAsync(tmp, 0, nz * 12 + (size_t)npts * 4, c->stream));
     TWXI_TRY(launch_gwr(*c, b, mth, nullptr, 0, nullptr, kmax, d_k, d_idx, d_z));
     uint8_t* st8;
-    TWXI_TRY(g_scratch[1].get((void**)&st8, npts));
+    TWXI_TRY(c->scratch[1].get((void**)&st8, npts));
     TWXI_TRY(launch_status_to_u8(c->stream, npts, b.status, st8));
     TWXI_TRY(copy_out(*c, z, d_z, nz));
     TWXI_TRY(copy_out(*c, idx, d_idx, nz));
@@ -590,7 +570,7 @@ int twxi_gwr_mth(twxi_ctx* c, const twxi_points* pts, int mth, const int32_t* nn
     TWXI_TRY(upload_override(*c, nnghs_override, npts, 2, &d_ovr));
     const int D = c->ob.moff[mth] - c->ob.moff[mth - 1];
     char* tmp;
-    TWXI_TRY(g_scratch[0].get((void**)&tmp, (size_t)npts * D * 8 + (size_t)npts * 8));
+    TWXI_TRY(c->scratch[0].get((void**)&tmp, (size_t)npts * D * 8 + (size_t)npts * 8));
     double* d_out = reinterpret_cast<double*>(tmp);
     double* d_ptn = d_out + (size_t)npts * D;
     TWXI_CUDA(cudaMemcpyAsync(d_ptn, pt_norm, (size_t)npts * 8, cudaMemcpyDefault, c->stream));
@@ -599,7 +579,7 @@ int twxi_gwr_mth(twxi_ctx* c, const twxi_points* pts, int mth, const int32_t* nn
     TWXI_TRY(launch_nngh_params(*c, b, nullptr, d_ovr, mth, 0, 1, 0));
     TWXI_TRY(launch_gwr(*c, b, mth, d_ptn, 0, d_out, 0, nullptr, nullptr, nullptr));
     uint8_t* st8;
-    TWXI_TRY(g_scratch[1].get((void**)&st8, npts));
+    TWXI_TRY(c->scratch[1].get((void**)&st8, npts));
     TWXI_TRY(launch_status_to_u8(c->stream, npts, b.status, st8));
     TWXI_TRY(copy_out(*c, out, d_out, (size_t)npts * D));
     TWXI_TRY(copy_out(*c, status, st8, (size_t)npts));
@@ -620,7 +600,7 @@ int twxi_interp_points(twxi_ctx* c, const twxi_points* pts, double* daily, doubl
     t.begin(c->stream);
     TWXI_TRY(run_variable(*c, daily != nullptr, &t));
     char* tmp;
-    TWXI_TRY(g_scratch[0].get((void**)&tmp, (size_t)npts * (12 * 8 * 3 + 1)));
+    TWXI_TRY(c->scratch[0].get((void**)&tmp, (size_t)npts * (12 * 8 * 3 + 1)));
     double* d_norms = reinterpret_cast<double*>(tmp);
     double* d_se = d_norms + (size_t)npts * 12;
     double* d_var = d_se + (size_t)npts * 12;
@@ -648,7 +628,8 @@ static int check_pair(twxi_ctx* a, twxi_ctx* b, bool daily) {
 
 int twxi_interp_cells(twxi_ctx* cmin, twxi_ctx* cmax, int ncells, const double* lat, const double* lon,
                       const double* elev, const double* tdi, const double* climdiv, const double* lst_tmin,
-                      const double* lst_tmax, const int32_t* rm_idx, int n_rm, int rm_zero_dist, int fix_invalid,
+                      const double* lst_tmax, const int32_t* rm_idx_tmin, const int32_t* rm_idx_tmax, int n_rm,
+                      int rm_zero_dist, int fix_invalid,
                       double* tmin, double* tmax, double* tmin_norms, double* tmax_norms, double* tmin_se,
                       double* tmax_se, int32_t* ninvalid, uint8_t* status, int mem) {
     TWXI_ARG(tmin && tmax && tmin_norms && tmax_norms && tmin_se && tmax_se && ninvalid && status, "null output");
@@ -658,15 +639,16 @@ int twxi_interp_cells(twxi_ctx* cmin, twxi_ctx* cmax, int ncells, const double* 
     cmax->stream = cmin->stream;
     int rc = TWXI_OK;
     do {
-        twxi_points pa{ncells, lat, lon, elev, tdi, lst_tmin, rm_idx, n_rm, rm_zero_dist};
-        twxi_points pb{ncells, lat, lon, elev, tdi, lst_tmax, rm_idx, n_rm, rm_zero_dist};
+        // leave-out indices are context-local: the tmin and tmax station tables are different subsets of the DB
+        twxi_points pa{ncells, lat, lon, elev, tdi, lst_tmin, rm_idx_tmin, n_rm, rm_zero_dist};
+        twxi_points pb{ncells, lat, lon, elev, tdi, lst_tmax, rm_idx_tmax, n_rm, rm_zero_dist};
         if ((rc = load_points(*cmin, &pa, default_k1(*cmin), true)) != TWXI_OK) break;
         if ((rc = load_points(*cmax, &pb, default_k1(*cmax), true)) != TWXI_OK) break;
         if (ncells == 0) break;
         const int nd = cmin->ob.ndays;
         if (climdiv) {
             double* d_cd;
-            if ((rc = g_scratch[2].get((void**)&d_cd, (size_t)ncells * 8)) != TWXI_OK) break;
+            if ((rc = cmin->scratch[2].get((void**)&d_cd, (size_t)ncells * 8)) != TWXI_OK) break;
             if (cudaMemcpyAsync(d_cd, climdiv, (size_t)ncells * 8, cudaMemcpyDefault, cmin->stream) != cudaSuccess) {
                 set_error("climdiv copy failed"); rc = TWXI_ERR_CUDA; break;
             }
@@ -680,7 +662,7 @@ int twxi_interp_cells(twxi_ctx* cmin, twxi_ctx* cmax, int ncells, const double* 
         tb.begin(cmin->stream);
         if ((rc = run_variable(*cmax, true, &tb)) != TWXI_OK) break;
         char* tmp;
-        if ((rc = g_scratch[0].get((void**)&tmp, (size_t)ncells * (12 * 8 * 4 + 4 + 1))) != TWXI_OK) break;
+        if ((rc = cmin->scratch[0].get((void**)&tmp, (size_t)ncells * (12 * 8 * 4 + 4 + 1))) != TWXI_OK) break;
         double* d_nmin = reinterpret_cast<double*>(tmp);
         double* d_nmax = d_nmin + (size_t)ncells * 12;
         double* d_semin = d_nmax + (size_t)ncells * 12;
@@ -732,22 +714,30 @@ static int interp_chunk_impl(twxi_ctx* cmin, twxi_ctx* cmax, const double* wrk_c
         const size_t wrk_bytes = (size_t)32 * ncell * 8;
         const double* d_wrk = wrk_chk;
         const bool acopy = async && host;                    // chunk and results travel on the copy streams
-        AsyncOut& ao = g_async;
-        if (acopy && (rc = ao.init(cmin->device)) != TWXI_OK) break;
+        AsyncOut& ao = cmin->async;
+        if (acopy && (rc = ao.init()) != TWXI_OK) break;
         if (acopy) {
             double* w;
             const int sl = ao.slot;
+            // The chunk submitted two calls ago used this slot.  Block the HOST until its work chunk has been read and its
+            // results are in the caller's buffers: this is what makes "valid after two further submissions" true
+            // (include/twxi.h).  The device still has the previous chunk queued, so no overlap is lost.
+            if (ao.inflight_in[sl] && cudaEventSynchronize(ao.loaded[sl]) != cudaSuccess) { set_error("event wait failed"); rc = TWXI_ERR_CUDA; break; }
+            ao.inflight_in[sl] = false;
+            if (ao.pending[sl] && cudaEventSynchronize(ao.copied[sl]) != cudaSuccess) { set_error("event wait failed"); rc = TWXI_ERR_CUDA; break; }
+            ao.pending[sl] = false;
             if ((rc = ao.win[sl].get((void**)&w, wrk_bytes)) != TWXI_OK) break;
             bool ok = true;
             if (ao.consumed[sl]) ok = cudaStreamWaitEvent(ao.h2d, ao.unpacked[sl], 0) == cudaSuccess;    // slot free again
             ok = ok && cudaMemcpyAsync(w, wrk_chk, wrk_bytes, cudaMemcpyHostToDevice, ao.h2d) == cudaSuccess;
             ok = ok && cudaEventRecord(ao.loaded[sl], ao.h2d) == cudaSuccess;
+            ao.inflight_in[sl] = ok;
             ok = ok && cudaStreamWaitEvent(cmin->stream, ao.loaded[sl], 0) == cudaSuccess;
             if (!ok) { set_error("wrk_chk copy failed"); rc = TWXI_ERR_CUDA; break; }
             d_wrk = w;
         } else if (host) {
             double* w;
-            if ((rc = g_scratch[2].get((void**)&w, wrk_bytes)) != TWXI_OK) break;
+            if ((rc = cmin->scratch[2].get((void**)&w, wrk_bytes)) != TWXI_OK) break;
             if (cudaMemcpyAsync(w, wrk_chk, wrk_bytes, cudaMemcpyHostToDevice, cmin->stream) != cudaSuccess) {
                 set_error("wrk_chk copy failed"); rc = TWXI_ERR_CUDA; break;
             }
@@ -760,7 +750,7 @@ static int interp_chunk_impl(twxi_ctx* cmin, twxi_ctx* cmax, const double* wrk_c
         uint8_t* d_st = status;
         if (host) {
             char* o;
-            Scratch& so = acopy ? ao.stage[ao.slot] : g_scratch[0];
+            Scratch& so = acopy ? ao.stage[ao.slot] : cmin->scratch[0];
             if ((rc = so.get((void**)&o, 2 * q_bytes + 4 * f_bytes + (size_t)ncell * 5 + 64)) != TWXI_OK) break;
             d_fnmin = reinterpret_cast<float*>(o); d_fnmax = d_fnmin + (size_t)12 * ncell;
             d_fsemin = d_fnmax + (size_t)12 * ncell; d_fsemax = d_fsemin + (size_t)12 * ncell;
@@ -781,9 +771,6 @@ static int interp_chunk_impl(twxi_ctx* cmin, twxi_ctx* cmax, const double* wrk_c
         ta.mark(5);
         tb.begin(cmin->stream);
         if ((rc = run_variable(*cmax, daily, &tb)) != TWXI_OK) break;
-        if (acopy && ao.pending[ao.slot]) {                  // the staging slot is still being drained (two calls ago)
-            if (cudaStreamWaitEvent(cmin->stream, ao.copied[ao.slot], 0) != cudaSuccess) { set_error("event wait failed"); rc = TWXI_ERR_CUDA; break; }
-        }
         if ((rc = launch_fixer(*cmin, *cmax, ncell, 1, daily ? 1 : 0, d_st, nullptr, nullptr, nullptr, nullptr, d_qmin,
                                d_qmax, d_fnmin, d_fnmax, d_fsemin, d_fsemax, d_ninv)) != TWXI_OK) break;
         tb.mark(5);
@@ -804,6 +791,7 @@ static int interp_chunk_impl(twxi_ctx* cmin, twxi_ctx* cmax, const double* wrk_c
             ao.pending[ao.slot] = true;
             ao.last = ao.slot;
             ao.slot ^= 1;
+            ++ao.submitted;
         } else if (host) {
             if ((rc = copy_out(*cmin, tmin, d_qmin, (size_t)nd * ncell)) != TWXI_OK) break;
             if ((rc = copy_out(*cmin, tmax, d_qmax, (size_t)nd * ncell)) != TWXI_OK) break;
@@ -839,12 +827,13 @@ int twxi_interp_chunk_async(twxi_ctx* cmin, twxi_ctx* cmax, const double* wrk_ch
 int twxi_interp_chunk_wait(twxi_ctx* cmin, int host_sync) {
     TWXI_ARG(cmin != nullptr, "null context");
     TWXI_CUDA(cudaSetDevice(cmin->device));
-    AsyncOut& ao = g_async;
+    AsyncOut& ao = cmin->async;
     if (ao.last >= 0) TWXI_CUDA(cudaStreamWaitEvent(cmin->stream, ao.copied[ao.last], 0));    // stream order: after the last copy
     if (host_sync) {
         TWXI_CUDA(cudaStreamSynchronize(cmin->stream));
         ao.pending[0] = ao.pending[1] = false;
         ao.consumed[0] = ao.consumed[1] = false;
+        ao.inflight_in[0] = ao.inflight_in[1] = false;
         ao.last = -1;
     }
     return TWXI_OK;

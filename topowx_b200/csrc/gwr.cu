@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(GWR_THREADS, 4) gwr_kernel(GwrArgs a) {
         s_z[warp][j] = zj;
         s_off[warp][j] = s * (int)nd;
         zn += zj * normm[s];
-        if (a.hat_z) {
+        if (a.hat_z && j < a.kmax) {                          // (device-resident overrides are not scanned on the host)
             a.hat_z[(size_t)q * a.kmax + j] = zj;
             a.hat_idx[(size_t)q * a.kmax + j] = s;
         }

@@ -331,7 +331,12 @@ struct KnnWork {                 // candidate lists of the gridded search, owned
     int32_t* cnt = nullptr;
     size_t cand_elems = 0, cnt_elems = 0;
 };
-static thread_local KnnWork g_knn;
+void knn_work_free(KnnWork* w) {
+    if (!w) return;
+    if (w->cand) cudaFree(w->cand);
+    if (w->cnt) cudaFree(w->cnt);
+    delete w;
+}
 constexpr int KNN_CAND_CAP = 1024;
 
 int launch_knn(Ctx& c, int npts, const double* lat, const double* lon, const int32_t* rm_idx, int n_rm,
@@ -344,7 +349,8 @@ int launch_knn(Ctx& c, int npts, const double* lat, const double* lon, const int
     a.cand = nullptr; a.cand_cnt = nullptr; a.cand_cap = 0; a.gx = 0; a.nbx = 0;
     // gridded queries without leave-outs: prune the station table once per block of cells
     if (gy > 0 && gx > 0 && (long long)gy * gx == npts && a.n_rm == 0 && !rm_zero && c.n > 2 * k1 && !getenv("TWXI_KNN_FULL")) {
-        KnnWork& w = g_knn;
+        if (!c.knn) c.knn = new KnnWork();
+        KnnWork& w = *c.knn;
         const int nby = (gy + KNN_BLK - 1) / KNN_BLK, nbx = (gx + KNN_BLK - 1) / KNN_BLK;
         const int cap = std::min(c.n, KNN_CAND_CAP);
         const size_t need = (size_t)nby * nbx * cap;

@@ -91,6 +91,49 @@ struct Batch {
     double* daily = nullptr;       // [cap][ndays] chronological order
 };
 
+// Grow-only device scratch buffer (results that need a type/layout conversion before leaving the library, staging).
+struct Scratch {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int get(void** out, size_t need) {
+        if (need > bytes) {
+            if (p) cudaFree(p);
+            p = nullptr; bytes = 0;
+            TWXI_CUDA(cudaMalloc(&p, need));
+            bytes = need;
+        }
+        *out = p;
+        return TWXI_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+// State of the asynchronous work-chunk call (twxi_interp_chunk_async), owned by the tmin context of the pair: results
+// leave the device on a copy stream from double-buffered staging, so that the device -> host copy of chunk t overlaps the
+// kernels of chunk t+1; work chunks go host -> device on their own stream into double-buffered staging, ahead of the kernels.
+struct AsyncOut {
+    cudaStream_t copy = nullptr;
+    cudaEvent_t done = nullptr;                   // compute stream: staging of the current call written
+    cudaEvent_t copied[2] = {nullptr, nullptr};   // copy stream: staging slot drained to the caller's buffers
+    bool pending[2] = {false, false};
+    Scratch stage[2];
+    cudaStream_t h2d = nullptr;
+    cudaEvent_t loaded[2] = {nullptr, nullptr};   // h2d stream: chunk staged
+    cudaEvent_t unpacked[2] = {nullptr, nullptr}; // compute stream: staged chunk consumed by unpack_chunk_kernel
+    bool consumed[2] = {false, false};
+    bool inflight_in[2] = {false, false};         // loaded[slot] recorded and not yet waited for on the host
+    Scratch win[2];
+    int slot = 0, last = -1;
+    long long submitted = 0;                      // chunks submitted so far
+    int init();
+    void destroy();
+};
+
+struct KedWork;                  // ked.cu: device scratch + launch configuration of the kriging stage
+struct KnnWork;                  // knn.cu: candidate lists of the gridded search
+void ked_work_free(KedWork*);
+void knn_work_free(KnnWork*);
+
 struct Ctx {
     int device = 0;
     cudaStream_t stream = 0;
@@ -104,6 +147,11 @@ struct Ctx {
     int n_climdivs = -1;           // -1: no check
     Batch b;
     int max_optim = 0;             // largest finite optim_nnghs / optim_nnghs_anom value
+    // device workspaces: owned by the context (one device, one stream), never shared between contexts
+    Scratch scratch[5];
+    AsyncOut async;
+    KedWork* ked = nullptr;
+    KnnWork* knn = nullptr;
 };
 
 // ---- stage launchers (each enqueues on ctx.stream) ----------------------------------------------------

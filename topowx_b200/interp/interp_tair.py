@@ -184,12 +184,12 @@ class PtInterpTair(object):
         a_pt = self.a_pt
         lst_tmin = np.array([a_pt["tmin%02d" % m] for m in range(1, 13)], dtype=np.float64)
         lst_tmax = np.array([a_pt["tmax%02d" % m] for m in range(1, 13)], dtype=np.float64)
+        # stns_rm names stations by id; each variable's context has its own index for them (interp_tair.py:565,574)
         rm_a = self.ctx_tmin.rm_indices(stns_rm)
         rm_b = self.ctx_tmax.rm_indices(stns_rm)
-        if rm_a is not None or rm_b is not None:
-            raise NotImplementedError("stns_rm with two station databases: use InterpTair.interp per variable")
         r = _context.interp_cells(self.ctx_tmin, self.ctx_tmax, a_pt[LAT], a_pt[LON], a_pt[ELEV], a_pt[TDI],
-                                  a_pt[CLIMDIV], lst_tmin, lst_tmax, fix_invalid=fix_invalid)
+                                  a_pt[CLIMDIV], lst_tmin, lst_tmax, rm_idx_tmin=rm_a, rm_idx_tmax=rm_b,
+                                  fix_invalid=fix_invalid)
         tmin, tmax, nmin, nmax, semin, semax, ninv, st = r
         _raise_status(st[0])
         for m in range(1, 13):                                    # side effects of the reference (:562-575, :433)

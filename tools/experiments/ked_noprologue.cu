@@ -4,38 +4,40 @@
 //
 // Math.  V_ij = C(h_ij), c0_j = C(h_0j) with C(0) = nug+psill, C(h>0) = psill*exp(-h/rng) (pure
 // nugget when rng == 0, interp.R:223-231), h = WGS-84 great-circle km (station-station from the table built at
-// context creation, point-station from the nngh_params stage).  With B = [X | y | c0] (n x 7; X = intercept +
+// context creation, point-station from the nngh_params stage).  With B = [X | c0 | y] (n x 7; X = intercept +
 // 4 drift columns centred on the prediction point and scaled — an exact reparametrisation because the
 // intercept is in X) the 7x7 matrix S = B' V^-1 B holds everything the predictor needs:
 //     G = X'V^-1X,  g_y = X'V^-1y,  g_c = X'V^-1c0,  s_cy = c0'V^-1y,  s_cc = c0'V^-1c0
 //     r = x0 - g_c,  G t = r,   mean = t'g_y + s_cy,   var = C(0) - s_cc + r't.
 //
 // Kernels.
-//  1. hgather: per point, the station-station distances of its nmax = max_m k_norm nearest stations are
-//     gathered ONCE from the N x N table into a compact buffer of row-major 8x8 tiles (lower block triangle,
-//     neighbours in distance-rank order so every month's set is a leading block).  The 12 monthly systems then
-//     stream their tiles with bulk copies instead of re-gathering 32-byte sectors per pair.
+//  1. ked_stage: per point, everything its 12 monthly systems read is staged ONCE in a compact buffer: the
+//     station-station distances of its nmax = max_m k_norm nearest stations as row-major 8x8 tiles (lower block triangle,
+//     neighbours in distance-rank order so every month's set is a leading block), the augmented rows -B' (month-independent
+//     part and per-month part), and per month the covariance parameters.  The solve kernel then needs no gathers at all:
+//     its inputs arrive by bulk copies (TMA) straight in the shared-memory slots they are consumed from.
 //  2. bin/scan/scatter: (point, month) problems are counting-sorted by NB = ceil(n/8) so that each size class
-//     is launched with exactly the shared memory it needs (occupancy 6 CTAs/SM at n ~ 80, 2 at n = 147).
+//     is launched with exactly the shared memory it needs.
 //  3. ked: persistent CTAs, one problem at a time per CTA, problems strided statically over the CTAs of the size
-//     class (the next problem's descriptor and neighbour indices are prefetched).  The augmented symmetric matrix
-//     [[V, B], [B', 0]] is eliminated with a LEFT-looking blocked Cholesky on 8x8 FP64 tiles held in the mma
-//     C-fragment layout (lane = 4*row + col/2 holds two adjacent columns): such a tile serves directly as the A
-//     operand and as the transposed B operand of two mma.sync.m8n8k4.f64 ("DMMA") steps, so X*Y' is two DMMAs and
-//     tiles never need re-layout.  Tile row NB holds B' (7 rows); its diagonal tile ends up as S.
+//     class.  The augmented symmetric matrix [[V, B], [B', 0]] is eliminated with a LEFT-looking blocked Cholesky on
+//     8x8 FP64 tiles held in the mma C-fragment layout (lane = 4*row + col/2 holds two adjacent columns): such a tile
+//     serves directly as the A operand and as the transposed B operand of two mma.sync.m8n8k4.f64 ("DMMA") steps, so
+//     X*Y' is two DMMAs and tiles never need re-layout.  Tile row NB holds B' (7 rows); its diagonal tile ends up as S.
 //     Data flow per problem (N := sum L L' - V, the negated Schur complement, so DMMAs accumulate in place):
-//       prologue   one thread issues a TMA bulk copy (cp.async.bulk + mbarrier) per tile row that lands the raw
-//                  distance tiles straight in the shared-memory slots of L; meanwhile all warps build B'; then one
-//                  pass turns every slot into -C(h) (ked_common.cuh: cov_pos).
+//       no prologue  the raw distance tiles of the problem were bulk-copied into the slots of L while the PREVIOUS
+//                  problem was being factored (a tile row is dead as soon as its block column has been used, and the next
+//                  problem of the CTA has the same layout), the augmented rows arrive while the first pivot tile is
+//                  factored, and every raw tile is turned into -C(h) in registers at the moment it is first consumed
+//                  (ked_common.cuh: cov_pos) — covariance arithmetic interleaves with the DMMA chains of the update.
 //       stage K    diagonal warp: -W = -inv(chol(D_K))' (chol8_inverse_t: fraction-free elimination of the pivot tile
-//                  as DMMA outer products), publish it; ONE CTA barrier; then it forms L(K+1,K) and D_{K+1} itself
-//                  and goes on factoring while the workers are busy with stage K.
+//                  as DMMA outer products), publish it; ONE CTA barrier; then it forms L(K+1,K) (published in place,
+//                  signalled on an mbarrier: the workers need it only at the end of a row pass) and D_{K+1} and goes on
+//                  factoring while the workers are busy with stage K.
 //                  workers (rows dealt round-robin per stage, two rows per pass = four independent DMMA chains):
-//                  L(I,K) = N(I,K)(-W)';  N(I,K+1) += sum_{J<=K} L(I,J) L(K+1,J)' (column K+1 is final after the
-//                  stage); the owner of row K+2 also forms the pivot tile N_diag(K+2).
-//     Nothing lives in registers across stages and the only synchronisation is one bar.sync per block column.
-//     Rejected variants (one warp per problem, right-looking register-resident, prologue-free with staged inputs) are
-//     archived under tools/experiments/ with their measurements in DESIGN.md §4.
+//                  L(I,K) = N(I,K)(-W)';  N(I,K+1) = -V(I,K+1) + sum_{J<=K} L(I,J) L(K+1,J)' (column K+1 is final after
+//                  the stage); the owner of row K+2 also forms the pivot tile N_diag(K+2).
+//     Nothing lives in registers across stages and the only CTA-wide synchronisation is one bar.sync per block column.
+//     The 5x5 GLS of a finished problem is run by a worker warp while the diagonal warp factors the next first pivot.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -44,28 +46,45 @@
 
 namespace twxi {
 
-constexpr int KED_HDR = 8 + 64 + 2 * 128;         // doubles: flag + mbarrier, 2^(j/64), -inv(L_KK) x2, N_diag x2
+constexpr int KED_HDR = 8 + 2 * KED_CP + KED_TABN + 2 * 128 + 64 + 8;   // doubles, see ked_kernel
 
-// ---- 1. compact distance tiles -------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) hgather_kernel(StnTable st, int q0, int nq, int k1, const int32_t* idx,
-                                                      const int32_t* nn, int32_t* status, double* hc,
-                                                      size_t hc_stride, int single_mth, int nbcap) {
-    __shared__ int sidx[256];
-    const int q = q0 + blockIdx.x;
-    if (status[q] != TWXI_ST_OK) return;
+// ---- 1. staged inputs of a point ----------------------------------------------------------------------------------
+struct StageArgs {
+    StnTable st;
+    int q0, nq, k1, single_mth, nbcap;
+    const int32_t* idx;
+    const int32_t* nn;
+    const double* h0;
+    const double* vario;       // [npts][12][3], or [npts][3] when vario_is_override
+    int vario_is_override;
+    const double *qlon, *qlat, *qelev, *qlst;
+    int32_t* status;
+    double* hc;
+    size_t hc_stride;
+    int off_bc, off_bm, off_cp;
+};
+
+__global__ void __launch_bounds__(256) ked_stage_kernel(StageArgs g) {
+    __shared__ int sidx[256], sraw[256];
+    const int q = g.q0 + blockIdx.x;
+    if (g.status[q] != TWXI_ST_OK) return;
     int nmax = 0;
     for (int m = 0; m < 12; ++m)
-        if (single_mth < 0 || m == single_mth) nmax = max(nmax, nn[(size_t)q * 24 + m]);
+        if (g.single_mth < 0 || m == g.single_mth) nmax = max(nmax, g.nn[(size_t)q * 24 + m]);
     if (nmax < 1) return;
-    if (nmax > 8 * nbcap) {                                   // larger than this build's kriging kernel serves
-        if (threadIdx.x == 0) atomicCAS(status + q, TWXI_ST_OK, TWXI_ST_LIMIT);
+    if (nmax > 8 * g.nbcap) {                                 // larger than this build's kriging kernel serves
+        if (threadIdx.x == 0) atomicCAS(g.status + q, TWXI_ST_OK, TWXI_ST_LIMIT);
         return;
     }
-    for (int j = threadIdx.x; j < nmax; j += blockDim.x) sidx[j] = st.hpos[idx[(size_t)q * k1 + j]];
+    for (int j = threadIdx.x; j < nmax; j += blockDim.x) {
+        const int s = g.idx[(size_t)q * g.k1 + j];
+        sraw[j] = s;
+        sidx[j] = g.st.hpos[s];
+    }
     __syncthreads();
     const int NB = (nmax + 7) >> 3;
-    const int N = st.n;
-    double* out = hc + (size_t)blockIdx.x * hc_stride;
+    const int N = g.st.n;
+    double* out = g.hc + (size_t)blockIdx.x * g.hc_stride;
     for (int I = 0; I < NB; ++I) {
         const int cnt = (I + 1) * 64;
         double* row = out + (size_t)htile(I, 0) * 64;
@@ -73,13 +92,58 @@ __global__ void __launch_bounds__(256) hgather_kernel(StnTable st, int q0, int n
             const int i = 8 * I + ((e >> 3) & 7), j = 8 * (e >> 6) + (e & 7);
             double h = 0.0;
             if (i < nmax && j < nmax && j != i) {             // diagonal tiles: both triangles
-                h = st.H[(size_t)sidx[i] * N + sidx[j]];
+                h = g.st.H[(size_t)sidx[i] * N + sidx[j]];
                 // two neighbours at the same location make V singular (gstat stops with an error, the drivers leave the
                 // fill value): decided here, exactly, instead of by the sign of a rounded pivot; the covariance
                 // evaluation of the solve then needs no h == 0 case
-                if (h == 0.0) atomicCAS(status + q, TWXI_ST_OK, TWXI_ST_SINGULAR);
+                if (h == 0.0) atomicCAS(g.status + q, TWXI_ST_OK, TWXI_ST_SINGULAR);
             }
             row[e] = h;
+        }
+    }
+    // ---- augmented rows, negated: -[1, dlon, dlat, delev] and the raw point-station distance (row 4 becomes -c0 in the
+    // solve), month-independent; predictors centred on the point and scaled (interp.R:256 FORMULA columns)
+    const double lon0 = g.qlon[q], lat0 = g.qlat[q], elev0 = g.qelev[q];
+    double* bc = out + g.off_bc;
+    for (int e = threadIdx.x; e < NB * KED_BC; e += blockDim.x) {
+        const int J = e / KED_BC, r = (e % KED_BC) >> 3, j = 8 * J + (e & 7);
+        double v = 0.0;
+        if (j < nmax) {
+            const int s = sraw[j];
+            if (r == 0) v = -1.0;
+            else if (r == 1) v = lon0 - g.st.lon[s];
+            else if (r == 2) v = lat0 - g.st.lat[s];
+            else if (r == 3) v = (elev0 - g.st.elev[s]) * 1e-3;
+            else v = g.h0[(size_t)q * g.k1 + j];
+        }
+        bc[e] = v;
+    }
+    // ---- per month: -[dlst, y - yref] and the covariance parameters
+    for (int m = 0; m < 12; ++m) {
+        if (g.single_mth >= 0 && m != g.single_mth) continue;
+        if (g.nn[(size_t)q * 24 + m] < 1) continue;
+        const double* lstm = g.st.lst + (size_t)m * N;
+        const double* normm = g.st.norm + (size_t)m * N;
+        const double lst0 = g.qlst[(size_t)q * 12 + m];
+        const double yref = normm[sraw[0]];
+        double* bm = out + g.off_bm + (size_t)m * g.nbcap * KED_BM;
+        for (int e = threadIdx.x; e < NB * KED_BM; e += blockDim.x) {
+            const int J = e / KED_BM, r = (e % KED_BM) >> 3, j = 8 * J + (e & 7);
+            double v = 0.0;
+            if (j < nmax) {
+                const int s = sraw[j];
+                v = r == 0 ? (lst0 - lstm[s]) * 0.1 : yref - normm[s];
+            }
+            bm[e] = v;
+        }
+        if (threadIdx.x == 0) {
+            const double* vp = g.vario_is_override ? g.vario + (size_t)q * 3 : g.vario + ((size_t)q * 12 + m) * 3;
+            CovPar cp;
+            covpar_set(cp, vp[0], vp[1], vp[2]);
+            double* c = out + g.off_cp + m * KED_CP;
+            c[0] = cp.c00; c[1] = cp.nir; c[2] = cp.nk; c[3] = cp.c0; c[4] = cp.c2; c[5] = cp.c3; c[6] = cp.c4; c[7] = cp.c5;
+            c[8] = yref;
+            for (int i = 9; i < KED_CP; ++i) c[i] = 0.0;
         }
     }
 }
@@ -160,7 +224,7 @@ __global__ void __launch_bounds__(256) ked_scatter_kernel(int q0, int nq, int si
 struct Prob {
     double2* tl2;          // lane's fragment pointer into the shared L / N tiles: tile t is tl2[t * 32]
     double2* Nd2;          // lane's fragment of the two N_diag buffers: Nd2[(c & 1) * 32]
-    const double2* hc2;    // lane's fragment pointer into the compact distance tiles of this point (global)
+    const double2* hc2;    // lane's fragment pointer into the staged distance tiles of this point (global)
     const double* tab32;
     CovPar cp;
     int NB, n, r8, q4;
@@ -173,28 +237,79 @@ __device__ __forceinline__ double2 neg_cov_diag(const Prob& p, int c, double2 hd
     return make_double2(-v.x, -v.y);
 }
 
+// Initial value of N(I,J), J < I, from the slot as the bulk copies left it.  V rows: -C(h), with the rows beyond n of the
+// last tile row zeroed (identity padding).  Augmented row I == NB: the staged -B' values; its row 4 holds the raw
+// point-station distances and becomes -c0 (nugget included at h == 0: exact interpolator), row 7 and the stations beyond
+// n are zero.
+__device__ __forceinline__ double2 init_tile(const Prob& p, int I, int J, double2 raw) {
+    if (I < p.NB) {
+        double2 v = make_double2(-cov_pos(raw.x, p.cp, p.tab32), -cov_pos(raw.y, p.cp, p.tab32));
+        if (I == p.NB - 1 && 8 * I + p.r8 >= p.n) v = make_double2(0.0, 0.0);
+        return v;
+    }
+    if (p.r8 == 4) raw = make_double2(-cov(raw.x, p.cp, p.tab32), -cov(raw.y, p.cp, p.tab32));
+    if (p.r8 == 7) raw = make_double2(0.0, 0.0);
+    if (J == p.NB - 1) {
+        const int j = 8 * J + 2 * p.q4;
+        if (j >= p.n) raw.x = 0.0;
+        if (j + 1 >= p.n) raw.y = 0.0;
+    }
+    return raw;
+}
+
+#ifdef TWXI_KED_PROFILE
+__device__ unsigned long long g_ked_prof[16];
+#define KPROF(i, v) do { if (lane == 0) atomicAdd(&g_ked_prof[i], (unsigned long long)(v)); } while (0)
+#define KCLK() clock64()
+#else
+#define KPROF(i, v) do { } while (0)
+#define KCLK() 0ll
+#endif
+
 // Stage K of a worker (rows I = K+2+u, K+2+u+NW, ..., two rows per pass: four independent DMMA chains):
-//   L(I,K)   = N(I,K) (-W)'                                          panel solve, stored in place
-//   N(I,K+1) += sum_{J<K} L(I,J) L(K+1,J)' + L(I,K) L(K+1,K)'        column K+1 is complete after this stage
+//   L(I,K)   = N(I,K) (-W)'                                              panel solve, stored in place
+//   N(I,K+1) = init + sum_{J<K} L(I,J) L(K+1,J)' + L(I,K) L(K+1,K)'       column K+1 is complete after this stage
 // and, by the owner of row K+2 (u == 0), the next-but-one pivot tile
 //   N_diag(K+2) = -V(K+2,K+2) + sum_{J<=K} L(K+2,J) L(K+2,J)'.
-// Every tile of the strict lower triangle is read and written exactly twice (update, then solve).
+// Column 0 (K == 0) is consumed straight from the bulk copies (init_tile).  Every tile of the strict lower triangle is
+// read twice and written twice (update, then solve).  L(K+1,K) comes from the diagonal warp (mbarrier `mbarL`).
 template <int NW>
-__device__ __forceinline__ void stage_rows(const Prob& p, int K, int u, const double2 negW, const double2 lk1, double2 vd) {
+__device__ __forceinline__ void stage_rows(const Prob& p, int K, int u, const double2 negW, double2 vd, void* mbarL,
+                                           uint32_t parL, long long& t_wait) {
     double2* tl2 = p.tl2;
     const double2* pB = tl2 + ltile(K + 1, 0) * 32;           // row K+1: L(K+1, J), J < K
     const int c = K + 2;
     int I = c + u;
     double2 lfirst = make_double2(0.0, 0.0);                  // L(K+2,K) of the u == 0 worker
+    double2 lk1 = make_double2(0.0, 0.0);
+    bool have_lk1 = false;
+#if !TWXI_KED_LK1_PUBLISHED
+    {
+        double2 nk1 = pB[K * 32];
+        if (K == 0) nk1 = init_tile(p, 1, 0, nk1);
+        dmma2(lk1, nk1, negW);                                // L(K+1,K), recomputed by every worker
+        have_lk1 = true;
+    }
+#endif
+    auto get_lk1 = [&]() {
+        if (!have_lk1) {
+            const long long t0 = KCLK();
+            mbar_wait(mbarL, parL);
+            t_wait += KCLK() - t0;
+            lk1 = pB[K * 32];
+            have_lk1 = true;
+        }
+    };
     for (; TWXI_KED_PAIR && I + NW <= p.NB; I += 2 * NW) {
         const int r1 = ltile(I, 0) * 32, r2 = ltile(I + NW, 0) * 32;
         const double2* pA1 = tl2 + r1;
         const double2* pA2 = tl2 + r2;
-        const double2 n1 = pA1[K * 32], n2 = pA2[K * 32];
-        double2 acc1 = pA1[K * 32 + 32], acc2 = pA2[K * 32 + 32];
+        double2 n1 = pA1[K * 32], n2 = pA2[K * 32];
+        if (K == 0) { n1 = init_tile(p, I, 0, n1); n2 = init_tile(p, I + NW, 0, n2); }
         double2 l1 = make_double2(0.0, 0.0), l2 = make_double2(0.0, 0.0);
         dmma(l1, n1.x, negW.x); dmma(l2, n2.x, negW.x);
         dmma(l1, n1.y, negW.y); dmma(l2, n2.y, negW.y);
+        double2 acc1 = init_tile(p, I, K + 1, pA1[K * 32 + 32]), acc2 = init_tile(p, I + NW, K + 1, pA2[K * 32 + 32]);
         double2 e1 = make_double2(0.0, 0.0), e2 = make_double2(0.0, 0.0);
         int J = 0;
         for (; J + 1 < K; J += 2) {
@@ -210,6 +325,7 @@ __device__ __forceinline__ void stage_rows(const Prob& p, int K, int u, const do
             dmma(acc1, a10.y, b0.y); dmma(acc2, a20.y, b0.y);
         }
         tl2[r1 + K * 32] = l1; tl2[r2 + K * 32] = l2;
+        get_lk1();
         dmma(e1, l1.x, lk1.x); dmma(e2, l2.x, lk1.x);
         dmma(e1, l1.y, lk1.y); dmma(e2, l2.y, lk1.y);
         acc1.x += e1.x; acc1.y += e1.y; acc2.x += e2.x; acc2.y += e2.y;
@@ -219,11 +335,11 @@ __device__ __forceinline__ void stage_rows(const Prob& p, int K, int u, const do
     for (; I <= p.NB; I += NW) {
         const int r1 = ltile(I, 0) * 32;
         const double2* pA1 = tl2 + r1;
-        const double2 n1 = pA1[K * 32];
-        double2 acc1 = make_double2(0.0, 0.0);
-        if (I > K + 1) acc1 = pA1[K * 32 + 32];
+        double2 n1 = pA1[K * 32];
+        if (K == 0) n1 = init_tile(p, I, 0, n1);
         double2 l1 = make_double2(0.0, 0.0);
         dmma2(l1, n1, negW);
+        double2 acc1 = init_tile(p, I, K + 1, pA1[K * 32 + 32]);
         double2 e1 = make_double2(0.0, 0.0);
         int J = 0;
         for (; J + 1 < K; J += 2) {
@@ -233,6 +349,7 @@ __device__ __forceinline__ void stage_rows(const Prob& p, int K, int u, const do
         }
         if (J < K) dmma2(acc1, pA1[J * 32], pB[J * 32]);
         tl2[r1 + K * 32] = l1;
+        get_lk1();
         dmma2(e1, l1, lk1);
         acc1.x += e1.x; acc1.y += e1.y;
         tl2[r1 + K * 32 + 32] = acc1;
@@ -254,36 +371,36 @@ __device__ __forceinline__ void stage_rows(const Prob& p, int K, int u, const do
     }
 }
 
-#ifdef TWXI_KED_PROFILE
-__device__ unsigned long long g_ked_prof[16];
-#define KPROF(i, v) do { if (lane == 0) atomicAdd(&g_ked_prof[i], (unsigned long long)(v)); } while (0)
-#define KCLK() clock64()
-#else
-#define KPROF(i, v) do { } while (0)
-#define KCLK() 0ll
-#endif
-
-template <int NW, int MINB, int NMAX>
+template <int NW, int MINB>
 __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
     extern __shared__ __align__(16) double sm[];
-    int* flag = reinterpret_cast<int*>(sm);                   // [0] singular
-    void* mbar = sm + 2;                                      // mbarrier of the distance-tile bulk copies
-    double* tab32 = sm + 8;                                   // 64: 2^(j/64)
-    double2* Wt2 = reinterpret_cast<double2*>(sm + 72);       // 2 x 64: -inv(L_KK), double-buffered by K & 1
-    double2* Nd2 = reinterpret_cast<double2*>(sm + 200);      // 2 x 64: N_diag of column c, double-buffered by c & 1
+    // header (doubles): 0 singular flag | 1 mbarV | 2 mbarB | 3 mbarL | 4..7 finish record (q, m, pending) |
+    //   8.. cpbuf 2 x 16 (covariance parameters + yref, double-buffered by problem) | tab 64 (2^(j/64)) |
+    //   Wt 2 x 64 (-inv(L_KK), by K & 1) | Nd 2 x 64 (N_diag of column c, by c & 1) | Sbuf 64 (S of the finished problem) | 8 pad
+    int* flag = reinterpret_cast<int*>(sm);
+    void* mbarV = sm + 1;                                     // distance tiles + parameters of a problem have landed
+    void* mbarB = sm + 2;                                     // augmented rows of the current problem have landed
+    void* mbarL = sm + 3;                                     // L(K+1,K) of the current stage published (32 arrivals)
+    int* fin = reinterpret_cast<int*>(sm + 4);                // [0] pending, [1] q, [2] m
+    double* cpbuf = sm + 8;
+    double* tab32 = cpbuf + 2 * KED_CP;
+    double2* Wt2 = reinterpret_cast<double2*>(tab32 + KED_TABN);
+    double2* Nd2 = Wt2 + 64;
+    double2* Sb2 = Nd2 + 64;
     double* tiles = sm + KED_HDR;
     constexpr int NT = (NW + 1) * 32;
-    constexpr int NJ = (NMAX + NT - 1) / NT;                  // stations per thread in the B' build (n <= NMAX)
 
     const int tid = threadIdx.x, lane = tid & 31;
-    int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform by construction
-    if (a.rot_sms > 0) warp = (warp + (int)blockIdx.x / a.rot_sms) % (NW + 1);      // role of this warp (NW = diagonal warp)
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);    // warp-uniform by construction; NW = diagonal warp
     const int NB = a.nbv;
     const int count = a.bcount[NB], start = a.bstart[NB];
-    const int N = a.st.n;
     for (int i = tid; i < KED_TABN; i += NT) tab32[i] = exp2((double)i / KED_TABN);
-    if (tid == 0) mbar_init(mbar, 1);
-    uint32_t parity = 0;
+    if (tid == 0) {
+        mbar_init(mbarV, 1); mbar_init(mbarB, 1); mbar_init(mbarL, 32);
+        mbar_init_fence();
+        fin[0] = 0;
+    }
+    uint32_t parV = 0, parB = 0, parL = 0;
 
     Prob p;
     p.tl2 = reinterpret_cast<double2*>(tiles) + lane;
@@ -291,144 +408,91 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
     p.tab32 = tab32;
     p.NB = NB; p.r8 = lane >> 2; p.q4 = lane & 3;
     double2* const tl2 = p.tl2;
-    const uint32_t tx_bytes = (uint32_t)(NB * (NB - 1) / 2) * 512u;     // tile rows 1..NB-1, I tiles each
+    const uint32_t v_bytes = (uint32_t)(NB * (NB - 1) / 2) * 512u + KED_CP * 8u;   // tile rows 1..NB-1 + parameters
+    const uint32_t b_bytes = (uint32_t)NB * (KED_BC + KED_BM) * 8u;
+    const int u = NW - 1 - warp;                              // workers: row-dealing offset (u == 0 owns the look-ahead)
 
-    // the 5x5 solve of a finished problem is deferred by the diagonal warp into the prologue of the next one
-    bool pending = false;
-    double2 pend_S = make_double2(0.0, 0.0);
-    int pend_q = 0, pend_m = 0;
-    double pend_yref = 0.0, pend_c00 = 0.0;
-
-    // software pipeline over problems: descriptor two ahead, neighbour indices one ahead
     int slot = blockIdx.x;
     if (slot >= count) return;
     int2 desc = a.list[start + slot];
     int2 desc_next = slot + (int)gridDim.x < count ? a.list[start + slot + gridDim.x] : make_int2(0, 0);
-    int sj[NJ], s_first;
+    // tid 0: bulk copies of the upcoming problem already issued (tile rows 1..pre; armed: expect_tx + parameters done)
+    int pre = 0;
+    bool armed = false;
+    int buf = 0;
+    // raw diagonal tiles: (0,0), (1,1) for the diagonal warp, (2,2) for the look-ahead worker; loaded one problem ahead
+    double2 hd = make_double2(0.0, 0.0), hd1 = make_double2(0.0, 0.0);
     {
-        const int32_t* ip = a.idx + (size_t)(desc.x / 12) * a.k1;
-        s_first = ip[0];
-#pragma unroll
-        for (int t = 0; t < NJ; ++t) sj[t] = (tid + t * NT < desc.y) ? ip[tid + t * NT] : 0;
+        const double2* h2 = reinterpret_cast<const double2*>(a.hc + (size_t)(desc.x / 12 - a.q0) * a.hc_stride) + lane;
+        if (warp == NW) {
+            hd = h2[0];
+            if (NB > 1) hd1 = h2[htile(1, 1) * 32];
+        } else if (u == 0 && NB > 2) {
+            hd = h2[htile(2, 2) * 32];
+        }
     }
-    for (; slot < count; slot += gridDim.x) {
+    __syncthreads();                                          // table, mbarriers
+    for (;;) {
         const int pid = desc.x, n = desc.y;
         const int q = pid / 12, m = pid - q * 12;
+        const bool has_next = slot + (int)gridDim.x < count;
+        int2 desc_next2 = make_int2(0, 0);                    // descriptor two problems ahead
+        if (slot + 2 * (int)gridDim.x < count) desc_next2 = a.list[start + slot + 2 * gridDim.x];
         p.n = n;
         const double* hc = a.hc + (size_t)(q - a.q0) * a.hc_stride;
+        const double* hc_next = a.hc + (size_t)(desc_next.x / 12 - a.q0) * a.hc_stride;
+        const int m_next = desc_next.x % 12;
         p.hc2 = reinterpret_cast<const double2*>(hc) + lane;
         const long long tp0 = KCLK();
         __syncthreads();                                      // previous problem: shared memory fully consumed
-        const long long tp1 = KCLK();
         if (tid == 0) {
-            flag[0] = 0;
-            if (tx_bytes) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_expect_tx(mbar, tx_bytes);
-                for (int I = 1; I < NB; ++I)
-                    bulk_g2s(tiles + ltile(I, 0) * 64, hc + htile(I, 0) * 64, (uint32_t)I * 512u, mbar);
+            fence_proxy_async();
+            if (!armed) {
+                mbar_expect_tx(mbarV, v_bytes);
+                bulk_g2s(cpbuf + buf * KED_CP, hc + a.off_cp + m * KED_CP, KED_CP * 8u, mbarV);
             }
-        }
-        // ---- augmented rows -B' = -[1, dlon, dlat, delev, dlst, y - yref, c0]' into tile row NB: one station per
-        // thread, all its gathers in flight at once (the indices were prefetched during the previous problem)
-        const double* lstm = a.st.lst + (size_t)m * N;
-        const double* normm = a.st.norm + (size_t)m * N;
-        const double yref = normm[s_first];
-        double gl[NJ][6];
-#pragma unroll
-        for (int t = 0; t < NJ; ++t) {
-            const int j = tid + t * NT;
-            if (j < n) {
-                const int s = sj[t];
-                gl[t][0] = a.st.lon[s]; gl[t][1] = a.st.lat[s]; gl[t][2] = a.st.elev[s];
-                gl[t][3] = lstm[s]; gl[t][4] = normm[s]; gl[t][5] = a.h0[(size_t)q * a.k1 + j];
+            for (int I = pre + 1; I < NB; ++I)
+                bulk_g2s(tiles + ltile(I, 0) * 64, hc + htile(I, 0) * 64, (uint32_t)I * 512u, mbarV);
+            mbar_expect_tx(mbarB, b_bytes);
+            double* rowB = tiles + ltile(NB, 0) * 64;
+            const double* bc = hc + a.off_bc;
+            const double* bm = hc + a.off_bm + (size_t)m * a.nbcap * KED_BM;
+            for (int J = 0; J < NB; ++J) {
+                bulk_g2s(rowB + J * 64, bc + J * KED_BC, KED_BC * 8u, mbarB);
+                bulk_g2s(rowB + J * 64 + KED_BC, bm + J * KED_BM, KED_BM * 8u, mbarB);
             }
+            pre = 0; armed = false;
         }
-        const double* vp = a.vario_is_override ? a.vario + (size_t)q * 3 : a.vario + ((size_t)q * 12 + m) * 3;
-        const double nug = vp[0], psill = vp[1], rng = vp[2];
-        const double lon0 = a.qlon[q], lat0 = a.qlat[q], elev0 = a.qelev[q], lst0 = a.qlst[(size_t)q * 12 + m];
-        // raw distances of the diagonal tiles 0, 1 (-> N_diag buffers) and 2 (first look-ahead column)
-        double2 hd = make_double2(0.0, 0.0), hd1 = make_double2(0.0, 0.0);
-        if (warp == NW) {                                     // the diagonal warp owns V(0,0) and V(1,1)
-            hd = p.hc2[0];
-            if (NB > 1) hd1 = p.hc2[htile(1, 1) * 32];
+        // the 5x5 GLS of the previous problem, by worker warp 0 while the diagonal warp factors the first pivot tile
+        if (warp == 0 && fin[0]) {
+            const double* cpo = cpbuf + (buf ^ 1) * KED_CP;
+            ked_finish(a.mean, a.var, a.status, Sb2[lane], fin[1], fin[2], cpo[8], cpo[0], lane);
         }
-        if (warp == NW - 1 && NB > 2) hd = p.hc2[htile(2, 2) * 32];     // look-ahead worker (u == 0)
-        covpar_set(p.cp, nug, psill, rng);
-        if (warp == NW && pending) {
-            ked_finish(a.mean, a.var, a.status, pend_S, pend_q, pend_m, pend_yref, pend_c00, lane);
-            pending = false;
-        }
+        mbar_wait(mbarV, parV);                               // distance tiles (prefetched) and parameters are here
+        parV ^= 1u;
         {
-            double* row = tiles + ltile(NB, 0) * 64;
-#pragma unroll
-            for (int t = 0; t < NJ; ++t) {
-                const int j = tid + t * NT;
-                if (j < 8 * NB) {
-                    double* col = row + (j >> 3) * 64 + (j & 7);
-                    const bool in = j < n;
-                    col[0] = in ? -1.0 : 0.0;
-                    col[8] = in ? lon0 - gl[t][0] : 0.0;
-                    col[16] = in ? lat0 - gl[t][1] : 0.0;
-                    col[24] = in ? (elev0 - gl[t][2]) * 1e-3 : 0.0;
-                    col[32] = in ? (lst0 - gl[t][3]) * 0.1 : 0.0;
-                    col[40] = in ? yref - gl[t][4] : 0.0;
-                    col[48] = in ? -cov(gl[t][5], p.cp, tab32) : 0.0;
-                    col[56] = 0.0;
-                }
-            }
+            const double* c = cpbuf + buf * KED_CP;
+            p.cp.c00 = c[0]; p.cp.nir = c[1]; p.cp.nk = c[2]; p.cp.c0 = c[3];
+            p.cp.c2 = c[4]; p.cp.c3 = c[5]; p.cp.c4 = c[6]; p.cp.c5 = c[7];
         }
-        // prefetch: descriptor two problems ahead, neighbour indices of the next problem
-        desc = desc_next;
-        if (slot + 2 * (int)gridDim.x < count) desc_next = a.list[start + slot + 2 * gridDim.x];
-        if (slot + (int)gridDim.x < count) {
-            const int32_t* ip = a.idx + (size_t)(desc.x / 12) * a.k1;
-            s_first = ip[0];
-#pragma unroll
-            for (int t = 0; t < NJ; ++t) sj[t] = (tid + t * NT < desc.y) ? ip[tid + t * NT] : 0;
-        }
-        const long long tp2 = KCLK();
-        if (tx_bytes) mbar_wait(mbar, parity);                // distance tiles have landed in their slots
-        parity ^= 1u;
-        const long long tp3 = KCLK();
-        // ---- covariances in place: slot <- -C(h).  Rows 1..NB-2 need no masking; two tiles per pass
-        {
-            const int T0 = NB >= 2 ? ltile(NB - 1, 0) : 0;
-            constexpr int NWT = NW + 1;
-            int t = warp;
-            for (; t + 3 * NWT < T0; t += 4 * NWT) {
-                const double2 h1 = tl2[t * 32], h2 = tl2[(t + NWT) * 32], h3 = tl2[(t + 2 * NWT) * 32], h4 = tl2[(t + 3 * NWT) * 32];
-                double2 v1, v2, v3, v4;
-                v1.x = -cov_pos(h1.x, p.cp, tab32); v2.x = -cov_pos(h2.x, p.cp, tab32); v3.x = -cov_pos(h3.x, p.cp, tab32); v4.x = -cov_pos(h4.x, p.cp, tab32);
-                v1.y = -cov_pos(h1.y, p.cp, tab32); v2.y = -cov_pos(h2.y, p.cp, tab32); v3.y = -cov_pos(h3.y, p.cp, tab32); v4.y = -cov_pos(h4.y, p.cp, tab32);
-                tl2[t * 32] = v1; tl2[(t + NWT) * 32] = v2; tl2[(t + 2 * NWT) * 32] = v3; tl2[(t + 3 * NWT) * 32] = v4;
-            }
-            for (; t < T0; t += NWT) {
-                const double2 h1 = tl2[t * 32];
-                tl2[t * 32] = make_double2(-cov_pos(h1.x, p.cp, tab32), -cov_pos(h1.y, p.cp, tab32));
-            }
-            const bool plain = 8 * NB <= n;                   // last row of V: identity padding beyond n
-            for (int c = warp; c < NB - 1; c += NW + 1) {
-                const double2 v = cov_tile(tl2[(T0 + c) * 32], 8 * (NB - 1) + p.r8, 8 * c + 2 * p.q4, n, p.cp, tab32, plain);
-                tl2[(T0 + c) * 32] = make_double2(-v.x, -v.y);
-            }
-            if (warp == NW) {
-                p.Nd2[0] = neg_cov_diag(p, 0, hd);
-                p.Nd2[32] = neg_cov_diag(p, 1, hd1);
-            }
-        }
-        const long long tp4 = KCLK();
-        __syncthreads();
-        const long long tp5 = KCLK();
-        if (warp == NW) { KPROF(0, 1); KPROF(1, tp5 - tp0); KPROF(2, tp2 - tp1); KPROF(3, tp4 - tp3); KPROF(13, tp3 - tp2); KPROF(14, tp1 - tp0); KPROF(15, tp5 - tp4); }
-        if (warp == 0) KPROF(8, 1);
+        const long long tp1 = KCLK();
         long long t_bar = 0, t_x = 0, t_y = 0;
-        (void)tp1; (void)tp2; (void)tp3; (void)tp4; (void)t_x; (void)t_y;
+        (void)tp0; (void)tp1; (void)t_x; (void)t_y;
 
         if (warp == NW) {
             // ================= diagonal warp =====================================================================
-            double2 D = Nd2[lane];
-            D.x = -D.x; D.y = -D.y;                           // V_00
+            if (lane == 0) flag[0] = 0;
+            double2 D;
+            {
+                const double2 v0 = neg_cov_diag(p, 0, hd);
+                D = make_double2(-v0.x, -v0.y);               // V_00
+                p.Nd2[32] = neg_cov_diag(p, 1, hd1);
+            }
+            if (has_next) {                                   // raw diagonal tiles of the next problem
+                const double2* h2 = reinterpret_cast<const double2*>(hc_next) + lane;
+                hd = h2[0];
+                if (NB > 1) hd1 = h2[htile(1, 1) * 32];
+            }
             bool singular = false;
             for (int K = 0; K < NB; ++K) {
                 double2 zt;
@@ -451,9 +515,18 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
                 t_bar += tb1 - tb0;
                 if (flag[0]) { singular = true; break; }
                 const double2 w = Wt2[(K & 1) * 32 + lane];
-                const int rb = ltile(K + 1, 0);
+                const int tk = ltile(K + 1, 0) + K;
+                double2 nk1 = tl2[tk * 32];                   // N(K+1,K): final after the workers' stage K-1
+                if (K == 0) {
+                    if (NB == 1) mbar_wait(mbarB, parB);      // (1,0) is an augmented tile
+                    nk1 = init_tile(p, 1, 0, nk1);
+                }
                 double2 l = make_double2(0.0, 0.0);
-                dmma2(l, tl2[(rb + K) * 32], w);              // L(K+1,K) = N(K+1,K) (-W)'
+                dmma2(l, nk1, w);                             // L(K+1,K) = N(K+1,K) (-W)'
+#if TWXI_KED_LK1_PUBLISHED
+                tl2[tk * 32] = l;
+                mbar_arrive(mbarL);
+#endif
                 double2 nd = Nd2[((K + 1) & 1) * 32 + lane];  // -V + sum_{J<K} L(K+1,J) L(K+1,J)'
                 dmma2(nd, l, l);
                 D.x = -nd.x; D.y = -nd.y;                     // D_{K+1}; for K+1 == NB this is -S
@@ -462,45 +535,75 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
 #endif
                 t_y += KCLK() - tb1;
             }
-            KPROF(4, KCLK() - tp5); KPROF(5, t_bar); KPROF(6, t_x); KPROF(7, t_y);
+            KPROF(0, 1); KPROF(1, tp1 - tp0); KPROF(4, KCLK() - tp1); KPROF(5, t_bar); KPROF(6, t_x); KPROF(7, t_y);
             if (singular) {
-                if (lane == 0) atomicCAS(a.status + q, TWXI_ST_OK, TWXI_ST_SINGULAR);
+                if (lane == 0) { atomicCAS(a.status + q, TWXI_ST_OK, TWXI_ST_SINGULAR); fin[0] = 0; }
             } else {
-                pend_S = make_double2(-D.x, -D.y);
-                pend_q = q; pend_m = m; pend_yref = yref; pend_c00 = p.cp.c00; pending = true;
+                Sb2[lane] = make_double2(-D.x, -D.y);
+                if (lane == 0) { fin[0] = 1; fin[1] = q; fin[2] = m; }
             }
         } else {
             // ================= worker warps ======================================================================
-            const int w = warp, u = NW - 1 - warp;           // phase A / phase B deal rows in opposite orders
             for (int K = 0; K < NB; ++K) {
                 const int c = K + 2;
                 double2 vd = make_double2(0.0, 0.0);
                 if (u == 0) {                                 // -V(c,c) before the barrier, next diagonal tile after it
                     vd = neg_cov_diag(p, c, hd);
                     if (c + 1 < NB) hd = p.hc2[htile(c + 1, c + 1) * 32];
+                    else if (has_next && c + 1 == NB && NB > 2)       // (2,2) of the next problem, one problem ahead
+                        hd = (reinterpret_cast<const double2*>(hc_next) + lane)[htile(2, 2) * 32];
                 }
                 const long long tb0 = KCLK();
                 named_bar_sync(1, NT);
                 const long long tb1 = KCLK();
                 t_bar += tb1 - tb0;
-                if (flag[0]) break;
+                if (K == 0) mbar_wait(mbarB, parB);           // augmented rows (issued at the top; the first pivot tile hid
+                                                              // them); waited for even when the problem is abandoned
+                if (flag[0]) {                                // singular pivot tile: the problem is abandoned by everybody
+                    if (u == 0 && has_next && NB > 2 && c + 1 <= NB)
+                        hd = (reinterpret_cast<const double2*>(hc_next) + lane)[htile(2, 2) * 32];
+                    break;
+                }
+#if TWXI_KED_PREFETCH
+                if (tid == 0 && has_next) {                   // tile row K died at this barrier: the next problem moves in
+                    if (K == 0) {
+                        fence_proxy_async();
+                        mbar_expect_tx(mbarV, v_bytes);
+                        bulk_g2s(cpbuf + (buf ^ 1) * KED_CP, hc_next + a.off_cp + m_next * KED_CP, KED_CP * 8u, mbarV);
+                        armed = true;
+                    } else {
+                        fence_proxy_async();
+                        bulk_g2s(tiles + ltile(K, 0) * 64, hc_next + htile(K, 0) * 64, (uint32_t)K * 512u, mbarV);
+                        pre = K;
+                    }
+                }
+#endif
                 if (c <= NB) {
                     const double2 negW = Wt2[(K & 1) * 32 + lane];
-                    double2 lk1 = make_double2(0.0, 0.0);
-                    dmma2(lk1, tl2[(ltile(K + 1, 0) + K) * 32], negW);     // L(K+1,K), recomputed by every worker
-                    stage_rows<NW>(p, K, u, negW, lk1, vd);
+                    stage_rows<NW>(p, K, u, negW, vd, mbarL, parL, t_y);
                     t_x += KCLK() - tb1;
                 }
+                parL ^= 1u;
             }
-            if (warp == 0) { KPROF(9, KCLK() - tp5); KPROF(10, t_bar); KPROF(11, t_x); KPROF(12, t_y); }
+            if (warp == 0) { KPROF(8, 1); KPROF(9, KCLK() - tp1); KPROF(10, t_bar); KPROF(11, t_x); KPROF(12, t_y); }
         }
+        parB ^= 1u;
+        if (!has_next) break;
+        slot += gridDim.x;
+        desc = desc_next;
+        desc_next = desc_next2;
+        buf ^= 1;
     }
-    if (warp == NW && pending) ked_finish(a.mean, a.var, a.status, pend_S, pend_q, pend_m, pend_yref, pend_c00, lane);
+    __syncthreads();
+    if (warp == 0 && fin[0]) {
+        const double* cpo = cpbuf + buf * KED_CP;
+        ked_finish(a.mean, a.var, a.status, Sb2[lane], fin[1], fin[2], cpo[8], cpo[0], lane);
+    }
 }
 
 static size_t ked_smem_for(int nbv) { return (size_t)(KED_HDR + (nbv * (nbv + 1) / 2) * 64) * sizeof(double); }
 
-struct KedWork {                 // device scratch of the kriging stage, owned per thread
+struct KedWork {                 // device scratch + launch configuration of the kriging stage, owned by the context
     double* hc = nullptr;
     size_t hc_bytes = 0;
     int2* list = nullptr;
@@ -513,20 +616,20 @@ struct KedWork {                 // device scratch of the kriging stage, owned p
     int var_for[KED_MAXNB + 1];  // variant chosen for each size class
 };
 
-// Launch variants: NW worker warps + the diagonal warp, minimum resident CTAs (register cap), largest n served.
+// Launch variants: NW worker warps + the diagonal warp, minimum resident CTAs (register cap).
 // Small systems have little panel work per pivot tile, so they run with fewer workers and more CTAs in flight: the
 // kernel is bound by the serial pivot chain of each problem times the problems resident per SM.
 struct KedVariant {
     void (*fn)(KedArgs);
-    int nw, nmax;
+    int nw;
 };
 static KedVariant KED_VARIANTS[] = {
-    {ked_kernel<1, 16, 64>, 1, 64},
-    {ked_kernel<2, 10, 96>, 2, 96},
-    {ked_kernel<3, 8, 128>, 3, 128},
-    {ked_kernel<3, 6, 128>, 3, 128},
-    {ked_kernel<5, 4, 192>, 5, 192},
-    {ked_kernel<7, 3, 255>, 7, 255},
+    {ked_kernel<1, 16>, 1},
+    {ked_kernel<2, 10>, 2},
+    {ked_kernel<3, 8>, 3},
+    {ked_kernel<3, 6>, 3},
+    {ked_kernel<5, 4>, 5},
+    {ked_kernel<7, 3>, 7},
 };
 constexpr int KED_NVARIANTS = sizeof(KED_VARIANTS) / sizeof(KED_VARIANTS[0]);
 void ked_work_free(KedWork* w) {
@@ -577,8 +680,8 @@ int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
         const int smem_max = (int)ked_smem_for(KED_NBMAX);
         for (int v = 0; v < KED_NVARIANTS; ++v)
             TWXI_CUDA(cudaFuncSetAttribute(KED_VARIANTS[v].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-        // default choice per size class (measured on B200, profiles/ked_variants_r01.txt); TWXI_KED_VAR overrides it with
-        // one digit (variant index) per size class NB = 1, 2, ...
+        // default choice per size class (measured on B200, profiles/); TWXI_KED_VAR overrides it with one digit (variant
+        // index) per size class NB = 1, 2, ...
         static const char* dflt = "000000002334443355555";
         const char* sel = getenv("TWXI_KED_VAR");
         if (!sel || (int)strlen(sel) < KED_NBMAX) sel = dflt;
@@ -591,17 +694,18 @@ int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
             }
             int v = sel[nb - 1] - '0';
             if (v < 0 || v >= KED_NVARIANTS) v = KED_NVARIANTS - 1;
-            while (KED_VARIANTS[v].nmax < 8 * nb && v + 1 < KED_NVARIANTS) ++v;   // the variant must cover n = 8 NB
-            if (KED_VARIANTS[v].nmax < 8 * nb) v = 5;
             w.var_for[nb] = v;
         }
         w.sms = p.multiProcessorCount;
     }
     // largest possible n is k1 - 1; points whose k_norm exceeds this build's limit (TWXI_MAX_KRIG_NNGHS) get TWXI_ST_LIMIT
-    // (hgather_kernel) instead of failing the whole call
+    // (ked_stage_kernel) instead of failing the whole call
     const int nbmax = std::min((b.k1 - 1 + 7) / 8, KED_NBMAX);
-    const size_t hc_stride = (size_t)nbmax * (nbmax + 1) / 2 * 64;
-    // points per sub-batch so that the compact distance buffer stays within its budget
+    const int off_bc = nbmax * (nbmax + 1) / 2 * 64;
+    const int off_bm = off_bc + nbmax * KED_BC;
+    const int off_cp = off_bm + 12 * nbmax * KED_BM;
+    const size_t hc_stride = (size_t)off_cp + 12 * KED_CP;
+    // points per sub-batch so that the staging buffer stays within its budget
     size_t budget = (size_t)6 << 30;
     if (const char* e = getenv("TWXI_HC_BUDGET_MB")) budget = (size_t)atoll(e) << 20;
     int qcap = (int)std::min<size_t>((size_t)b.npts, std::max<size_t>(1, budget / (hc_stride * 8)));
@@ -625,20 +729,24 @@ int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
         w.blockcnt_cap = nblk_cap;
     }
     int32_t *bcount = w.bins, *bstart = w.bins + (KED_MAXNB + 1);
-    KedArgs a;
-    a.st = c.st; a.npts = b.npts; a.k1 = b.k1;
-    a.idx = b.idx; a.h0 = b.h0; a.nn = b.nn;
-    a.vario = vario_override ? vario_override : b.vario;
-    a.vario_is_override = vario_override != nullptr;
-    a.qlon = b.lon; a.qlat = b.lat; a.qelev = b.elev; a.qlst = b.lst;
-    a.hc = w.hc; a.hc_stride = hc_stride; a.list = w.list; a.bstart = bstart; a.bcount = bcount;
-    a.mean = b.mean; a.var = b.var; a.status = b.status;
-    a.rot_sms = 0;
     const int single = mth >= 1 ? mth - 1 : -1;
+    StageArgs g;
+    g.st = c.st; g.k1 = b.k1; g.single_mth = single; g.nbcap = nbmax;
+    g.idx = b.idx; g.nn = b.nn; g.h0 = b.h0;
+    g.vario = vario_override ? vario_override : b.vario;
+    g.vario_is_override = vario_override != nullptr;
+    g.qlon = b.lon; g.qlat = b.lat; g.qelev = b.elev; g.qlst = b.lst;
+    g.status = b.status; g.hc = w.hc; g.hc_stride = hc_stride;
+    g.off_bc = off_bc; g.off_bm = off_bm; g.off_cp = off_cp;
+    KedArgs a;
+    a.npts = b.npts;
+    a.hc = w.hc; a.hc_stride = hc_stride; a.off_bc = off_bc; a.off_bm = off_bm; a.off_cp = off_cp; a.nbcap = nbmax;
+    a.list = w.list; a.bstart = bstart; a.bcount = bcount;
+    a.mean = b.mean; a.var = b.var; a.status = b.status;
     for (int q0 = 0; q0 < b.npts; q0 += qcap) {
         const int nq = std::min(qcap, b.npts - q0);
-        a.q0 = q0;
-        hgather_kernel<<<nq, 256, 0, c.stream>>>(c.st, q0, nq, b.k1, b.idx, b.nn, b.status, w.hc, hc_stride, mth >= 1 ? mth - 1 : -1, nbmax);
+        a.q0 = q0; g.q0 = q0; g.nq = nq;
+        ked_stage_kernel<<<nq, 256, 0, c.stream>>>(g);
         TWXI_LAUNCH_CHECK();
         const int nt = nq * 12, nblk = (nt + 255) / 256;
         ked_bin_kernel<<<nblk, 256, 0, c.stream>>>(q0, nq, single, b.nn, b.status, w.blockcnt);
@@ -658,9 +766,8 @@ int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
         for (int nbv = nbmax; nbv >= 1; --nbv) {
             a.nbv = nbv;
             const int v = w.var_for[nbv];
-            const size_t smem = ked_smem_for(nbv);
             const int grid = std::min(w.sms * w.occ[v][nbv], std::max(1, nt));
-            KED_VARIANTS[v].fn<<<grid, (KED_VARIANTS[v].nw + 1) * 32, smem, c.stream>>>(a);
+            KED_VARIANTS[v].fn<<<grid, (KED_VARIANTS[v].nw + 1) * 32, ked_smem_for(nbv), c.stream>>>(a);
             TWXI_LAUNCH_CHECK();
         }
         if (timed) {

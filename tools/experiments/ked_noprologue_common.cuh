@@ -10,45 +10,48 @@ namespace twxi {
 #ifndef TWXI_KED_PAIR
 #define TWXI_KED_PAIR 1          // workers update two tile rows per pass (four independent DMMA chains)
 #endif
+#ifndef TWXI_KED_LK1_PUBLISHED
+#define TWXI_KED_LK1_PUBLISHED 1 // L(K+1,K) formed once by the diagonal warp (0: every worker recomputes it)
+#endif
+#ifndef TWXI_KED_PREFETCH
+#define TWXI_KED_PREFETCH 1      // the next problem's distance tiles are bulk-copied into tile rows as they die
+#endif
 
 constexpr int KED_MAXNB = 32;           // size classes NBv = 1..32 (n <= 255)
 
+// Staged inputs of one point (written by ked_stage_kernel, read by ked_kernel with bulk copies), in doubles from the
+// point's base `hc + (q - q0) * hc_stride`:
+//   [0, off_bc)                 distance tiles: rows 0..NB-1, row I holds tiles J = 0..I (8x8 row-major)   htile()
+//   [off_bc, off_bm)            per tile column J: 5 x 8   -[1, dlon, dlat, delev] and the raw point-station distance h0
+//   [off_bm, off_cp)            per month m, per tile column J: 2 x 8   -[dlst_m, y_m - yref_m]
+//   [off_cp, hc_stride)         per month m: 16 doubles  CovPar (8) | yref | padding
+constexpr int KED_BC = 40, KED_BM = 16, KED_CP = 16;
+
 struct KedArgs {
-    StnTable st;
-    int npts, k1, q0;
-    const int32_t* idx;
-    const double* h0;
-    const int32_t* nn;
-    const double* vario;       // [npts][12][3], or [npts][3] when vario_is_override
-    int vario_is_override;
-    const double* qlon;
-    const double* qlat;
-    const double* qelev;
-    const double* qlst;        // [npts][12]
-    const double* hc;          // compact distance tiles of points q0.. (stride hc_stride doubles per point)
+    int npts, q0;
+    const double* hc;          // staged inputs of points q0.. (stride hc_stride doubles per point)
     size_t hc_stride;
+    int off_bc, off_bm, off_cp, nbcap;
     const int2* list;          // (problem id q*12 + m, n) sorted by size class
     const int32_t* bstart;     // [KED_MAXNB+1]
     const int32_t* bcount;
     int nbv;                   // size class of this launch
-    int rot_sms;               // > 0: warp roles rotate with blockIdx.x / rot_sms (the CTA's residency slot on its SM), so that
-                               // the diagonal warps of the CTAs of one SM sit on different SM sub-partitions
     double* mean;              // [npts][12]
     double* var;
     int32_t* status;
 };
 
 // shared-memory L tiles: rows 1..NBv, row I holds tiles J = 0..I-1 (diagonal tiles are never stored)
-__device__ __forceinline__ int ltile(int I, int J) { return I * (I - 1) / 2 + J; }
+__host__ __device__ __forceinline__ int ltile(int I, int J) { return I * (I - 1) / 2 + J; }
 // compact distance tiles: rows 0..NB-1, row I holds tiles J = 0..I
-__device__ __forceinline__ int htile(int I, int J) { return I * (I + 1) / 2 + J; }
+__host__ __device__ __forceinline__ int htile(int I, int J) { return I * (I + 1) / 2 + J; }
 
 
-// ---- covariances, barrier / bulk-copy helpers, the 5x5 GLS --------------------------------------------------------
-// Covariances.  psill * exp(-h / range) for h >= 0 with ~1e-16 relative error: with t = -h / range,
-// t = k ln2/64 + r (|r| <= ln2/128), exp(t) = 2^(k >> 6) * 2^((k & 63)/64) * P5(r); psill is folded into the
-// coefficients of P5, the power-of-two table lives in shared memory.  Branch-free: 10 FP64 operations, one table
-// lookup and five integer operations per value (this is a third of all the instructions of the kriging kernel).
+// ---- covariances ------------------------------------------------------------------------------------------------
+// psill * exp(-h / range) for h >= 0 with ~1e-16 relative error: with t = -h / range, t = k ln2/64 + r
+// (|r| <= ln2/128), exp(t) = 2^(k >> 6) * 2^((k & 63)/64) * P5(r); psill is folded into the coefficients of P5, the
+// power-of-two table lives in shared memory.  Branch-free: 11 FP64 operations, one table lookup and five integer
+// operations per value.
 constexpr int KED_TABN = 64;
 struct CovPar {
     double c00;                      // C(0) = nugget + partial sill
@@ -96,10 +99,10 @@ __device__ __forceinline__ double cov(double h, const CovPar& cp, const double* 
 // `plain` (warp-uniform): the tile is strictly below the diagonal and inside the n x n block, so no masking.
 __device__ __forceinline__ double2 cov_tile(double2 h, int i, int j, int n, const CovPar& cp, const double* tab32,
                                             bool plain) {
-    double2 v;                                                // (co-located station pairs never get here: hgather)
+    double2 v;                                                // (co-located station pairs never get here: ked_stage_kernel)
     v.x = cov_pos(h.x, cp, tab32);
     v.y = cov_pos(h.y, cp, tab32);
-    if (!plain) {                                             // diagonal tiles are kept fully symmetric (elim8_mma)
+    if (!plain) {                                             // diagonal tiles are kept fully symmetric (chol8_inverse_t)
         if (j == i) v.x = cp.c00;
         if (j + 1 == i) v.y = cp.c00;
         if (i >= n || j >= n) v.x = (i == j) ? 1.0 : 0.0;     // identity padding
@@ -108,16 +111,20 @@ __device__ __forceinline__ double2 cov_tile(double2 h, int i, int j, int n, cons
     return v;
 }
 
+// ---- barriers, bulk copies ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(void* mbar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(void* mbar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(void* mbar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(mbar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(void* mbar, uint32_t parity) {
     uint32_t done;
@@ -126,33 +133,52 @@ __device__ __forceinline__ void mbar_wait(void* mbar, uint32_t parity) {
                      : "=r"(done) : "r"(smem_u32(mbar)), "r"(parity) : "memory");
     } while (!done);
 }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // TMA 1-D bulk copy global -> shared, completion signalled on the mbarrier (bytes and addresses multiples of 16)
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, void* mbar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
 }
 
-// 16-byte asynchronous copy global -> shared (lane-private slots: the issuing lane is the only reader)
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+// ---- 5x5 GLS ----------------------------------------------------------------------------------------------------------
+// S = B'V^-1B held by one warp in C-fragment layout, rows / columns in the order of the staged augmented rows
+//     0..3 = [1, dlon, dlat, delev],  4 = c0,  5 = dlst,  6 = y - yref,  7 = padding,
+// i.e. the drift block G has indices {0,1,2,3,5}.  Bordering G with g_y and -(x0 - g_c) (x0 = e_0: the drift columns are
+// centred on the prediction point) and eliminating the five drift pivots leaves
+//     T[6][4] = s_cy + g_y' G^-1 (x0 - g_c) = mean - yref,     T[4][4] = -(x0 - g_c)' G^-1 (x0 - g_c),
+// so var = C(0) - s_cc - T[4][4].  The elimination runs on the tensor pipe like the pivot tiles (same fraction-free scheme
+// as chol8_inverse_t, twxi_internal.cuh).
+__device__ __forceinline__ bool elim_drift_pivots(double2& a, int lane) {
+    const int q = lane & 3;
+    bool ok = true;
+    double rprev = 1.0;                                       // 1 / previous pivot
+#pragma unroll
+    for (int t = 0; t < 5; ++t) {
+        const int k = t < 4 ? t : 5;
+        const int kq = k >> 1;
+        const double mine = (k & 1) ? a.y : a.x;
+        const double e = (q == kq) ? mine : 0.0;              // M[r][k] in the lanes that own column k
+        const double dk = __shfl_sync(0xffffffffu, mine, 4 * k + kq);
+        ok = ok && (dk > 0.0);
+        const double es = -e * rprev;
+        const double piv = dk * rprev;
+        double2 c = make_double2(piv * a.x, piv * a.y);       // M <- (d_k M - M[:,k] M[:,k]') / previous pivot
+        dmma(c, es, e);
+        a = c;
+        rprev = fast_rcp(dk);
+    }
+    a.x *= rprev; a.y *= rprev;                               // Schur complement of the five drift pivots
+    return ok;
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-// 5x5 GLS from S = B'V^-1B held by one warp in C-fragment layout: mean and variance of the kriging predictor.
-// S = [[G, g_y, g_c], [., ., s_cy], [., ., s_cc]] (row/column 7 are padding).  Bordering G with g_y and -(x0 - g_c)
-// (x0 = e_0: the drift columns are centred on the prediction point) and eliminating its 5 pivots leaves
-//     T[5][6] = s_cy + g_y' G^-1 (x0 - g_c) = mean - yref,     T[6][6] = -(x0 - g_c)' G^-1 (x0 - g_c),
-// so var = C(0) - s_cc - T[6][6].  The elimination runs on the tensor pipe like the pivot tiles (elim8_mma).
 __device__ __forceinline__ void ked_finish(double* mean_out, double* var_out, int32_t* status, double2 s0, int q, int m,
                                            double yref, double c00, int lane) {
-    const double scc = s0.x;                                  // S[6][6] in lane 27
-    if (lane == 4 * 6 + 0 || lane == 4 * 0 + 3) s0.x -= 1.0;  // (6,0) and (0,6): g_c - x0
-    if (lane == 4 * 6 + 3) s0.x = 0.0;                        // (6,6)
-    const bool ok = elim8_mma<5>(s0, lane);
-    const double t56 = __shfl_sync(0xffffffffu, s0.x, 4 * 5 + 3);
-    if (lane == 4 * 6 + 3) {
-        const double mean = t56 + yref, var = c00 - scc - s0.x;
+    const double scc = s0.x;                                  // S[4][4] in lane 18
+    if (lane == 4 * 4 + 0 || lane == 4 * 0 + 2) s0.x -= 1.0;  // (4,0) and (0,4): g_c - x0
+    if (lane == 4 * 4 + 2) s0.x = 0.0;                        // (4,4)
+    const bool ok = elim_drift_pivots(s0, lane);
+    const double t64 = __shfl_sync(0xffffffffu, s0.x, 4 * 6 + 2);
+    if (lane == 4 * 4 + 2) {
+        const double mean = t64 + yref, var = c00 - scc - s0.x;
         if (!ok || !isfinite(mean) || !isfinite(var)) {
             atomicCAS(status + q, TWXI_ST_OK, TWXI_ST_SINGULAR);
         } else {

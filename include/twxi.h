@@ -166,6 +166,27 @@ int twxi_krig(twxi_ctx* ctx, const twxi_points* pts, int mth,
               double* mean, double* var, uint8_t* status, int mem);
 
 /*
+ * moving-window variogram fitting.  Replaces BuildKrigParams.get_krig_params
+ * (interp_tair.py:612-698) and the R function get_vario_params (interp.R:54-113: OLS residuals -> gstat sample
+ * variogram in 5 km lags up to 1.4 x the neighbourhood radius -> exponential model with nugget = min(gamma) and the
+ * sill fixed, range fitted with fit.method 7 weights -> GLS residuals -> second variogram and fit) for npts points.
+ *   mth 1..12 = that month (vario [npts][1][3]); 0 = all months ([npts][12][3]); values (nugget, psill, range), a pure
+ *   nugget is (sill, 0, 0) (interp.R:103-107); NaN for failed points.
+ *   nnghs_override int32 [npts] or NULL = the smoothed optimal count (interp_tair.py:666-678)
+ */
+int twxi_fit_vario(twxi_ctx* ctx, const twxi_points* pts, int mth, const int32_t* nnghs_override,
+                   double* vario, uint8_t* status, int mem);
+
+/*
+ * SURVEY 8f rank 2 (step 21): variogram fit + regression kriging in one step for all 12 months with a given neighbour
+ * count per point.  Replaces KrigTairAll.krigall (interp_tair.py:700-768) / R krig_all (interp.R:147-159); with
+ * rm_idx = the station itself and rm_zero_dist = 1 it is the body of XvalTairNorm.run_xval (optimize.py:239-266).
+ * nnghs int32 [npts]; outputs float64 mean, var [npts][12], vario [npts][12][3] (may be NULL), status uint8 [npts].
+ */
+int twxi_krig_all(twxi_ctx* ctx, const twxi_points* pts, const int32_t* nnghs,
+                  double* mean, double* var, double* vario, uint8_t* status, int mem);
+
+/*
  * Stage a8-a9 (weights only): GWR hat rows.  For month mth (1..12) returns, per point, the neighbour count
  * k, the k neighbour indices in ascending (distance, index) order and the row z = x'(X'WX)^-1 X'W of
  * _gwr_series (interp_tair.py:1128-1140) in that same order.  idx int32 / z float64 are [npts][kmax].
@@ -190,6 +211,18 @@ int twxi_gwr_mth(twxi_ctx* ctx, const twxi_points* pts, int mth, const int32_t* 
  */
 int twxi_interp_points(twxi_ctx* ctx, const twxi_points* pts, double* daily, double* norms, double* se,
                        double* var, uint8_t* status, int mem);
+
+/*
+ * Cross validation of the GWR neighbour count.  Replaces XvalTairAnom.run_xval
+ * (twx/interp/optimize.py:505-545) for npts stations at once: every point IS a station of the context (stn_idx int32
+ * [npts], indices into the context's table; the station record is the `pt`), it is left out of its own neighbour search
+ * together with any co-located station (rm_zero_dist_stns=True, optimize.py:499), the neighbour search runs once with the
+ * largest count, and for every count of nnghs (HOST array, int32 [n_counts], 6..TWXI_MAX_NNGHS) and every month the daily
+ * anomalies are interpolated with GWR and compared with the station's own: bias = mean(interp - obs), mae, r2 =
+ * linregress r^2.  Outputs float64 [npts][n_counts][12] (NaN for stations that fail), status uint8 [npts].
+ */
+int twxi_xval_anom(twxi_ctx* ctx, int npts, const int32_t* stn_idx, int n_counts, const int32_t* nnghs,
+                   double* bias, double* mae, double* r2, uint8_t* status, int mem);
 
 /*
  * a11 / a12: Tmin and Tmax at ncells points with the Tmin>=Tmax fixer.  Replaces PtInterpTair.interp_pt
@@ -254,6 +287,12 @@ int twxi_get_stage_ms(float* ms5);
  * bench.py divides the algorithmic FLOPs of the kriging systems by this figure for its roofline object.
  */
 int twxi_get_ked_kernel_ms(float* ms);
+
+/*
+ * Instrumentation: which = 0 -> mean number of candidate stations per block of cells in the most recent gridded
+ * neighbour search of this context (the N_c of SURVEY 8d's F_knn = 25 N_c; -1 when no gridded search has run).
+ */
+int twxi_ctx_stat(twxi_ctx* ctx, int which, double* out);
 
 /*
  * Measured FP64 peak of `device` in TFLOP/s: tensor-core DMMA (mma.sync.m8n8k4.f64) and scalar DFMA loops.

@@ -55,3 +55,24 @@ def run_sample(da_tmin, da_tmax, wrk_chk, cells, nworkers=None):
         res = pool.map(_work, chunks, chunksize=1)
         wall = time.perf_counter() - t0
     return sum(r[0] for r in res), wall, nworkers
+
+
+def _work_full(cells):
+    out = o.interp_chunk(_G["pti"], _G["wrk"], cells=cells)
+    keys = ("tmin", "tmax", "tmin_norm", "tmax_norm", "tmin_se", "tmax_se")
+    return [(rc, int(out["status"][rc]), int(out["ninvalid"][rc]), {k: out[k][:, rc[0], rc[1]].copy() for k in keys})
+            for rc in cells]
+
+
+def interp_cells_parallel(da_tmin, da_tmax, wrk_chk, cells, nworkers=None):
+    """The oracle's step25 loop on ``cells`` of ``wrk_chk`` over a process pool (parity tests with hundreds of cells).
+    Returns {(r, c): (status, ninvalid, {name: per-cell vector})}."""
+    nworkers = nworkers or default_workers()
+    chunks = [cells[i::nworkers * 2] for i in range(nworkers * 2)]
+    chunks = [c for c in chunks if c]
+    ctx = mp.get_context("fork")
+    days = np.array(da_tmin.days[[o.YEAR, o.MONTH]])
+    with ctx.Pool(nworkers, initializer=_init,
+                  initargs=(da_tmin.stns, da_tmin.var, da_tmax.stns, da_tmax.var, days, wrk_chk)) as pool:
+        res = pool.map(_work_full, chunks, chunksize=1)
+    return {rc: (st, ninv, vals) for part in res for (rc, st, ninv, vals) in part}

@@ -526,3 +526,185 @@ class XvalTairAnom(object):
                 r_value = np.corrcoef(interp_anom, xval_anom)[0, 1]      # = stats.linregress(...)[2] (:530)
                 r2[x, mth - 1] = r_value ** 2
         return bias, mae, r2
+
+
+# ------------------------------------------------------------------------------------------------
+# f3  variogram fitting: R get_vario_params / krig_all (twx/interp/rpy/interp.R:54-113, 147-159, 290-428)
+#     [EXT: gstat variogram(), fit.variogram(fit.method=7), predict(BLUE=TRUE)]  PARITY UNPINNED against real gstat.
+VARIO_WIDTH_KM = 5.0                                   # interp.R:64 width=5
+FIT_LIMIT, FIT_MAXIT = 1e-6, 200                       # gstat defaults: set(fit_limit=1e-6), set(iter=200)
+
+
+def sample_variogram(H, z, cutoff, width=VARIO_WIDTH_KM):
+    """gstat ``variogram(z~trend, cutoff=, width=)`` on residuals ``z`` with pair distances ``H`` (great-circle km for
+    long/lat data): pairs with h <= cutoff go to lag floor(h / width); per non-empty lag: np, mean distance,
+    gamma = sum (z_i - z_j)^2 / (2 np).  Returns (np, dist, gamma) for the non-empty lags in lag order."""
+    n = z.size
+    iu = np.triu_indices(n, 1)
+    h = H[iu]
+    d2 = (z[iu[0]] - z[iu[1]]) ** 2
+    keep = h <= cutoff
+    h, d2 = h[keep], d2[keep]
+    lag = np.floor(h / width).astype(np.int64)
+    nb = int(np.floor(cutoff / width)) + 1
+    cnt = np.bincount(lag, minlength=nb)
+    sh = np.bincount(lag, weights=h, minlength=nb)
+    sg = np.bincount(lag, weights=d2, minlength=nb)
+    ok = cnt > 0
+    return cnt[ok].astype(np.float64), sh[ok] / cnt[ok], sg[ok] / (2.0 * cnt[ok])
+
+
+def fit_exp_range(npairs, dist, gamma, nugget, sill):
+    """``my.autofit.gwvario(avar, model="Exp", fix.values=c(nugget, NA, sill), fit.method=7)`` (interp.R:68,87,290-428):
+    exponential model gamma(h) = nugget + psill (1 - exp(-h / range)) with nugget and psill = sill - nugget fixed, the
+    range fitted by weighted least squares with weights N_j / h_j^2 (gstat fit.method 7), Gauss-Newton from
+    range0 = 0.1 max(dist) (interp.R:311), steps halved while the error grows, stop when the relative change of the
+    weighted SSE is below 1e-6 or after 200 iterations - continued here to the minimiser itself (|step| <= 1e-10 range).
+    Returns (nugget, psill, range) or None where the R code falls
+    back to a pure nugget (fit error, negative psill or range: interp.R:69-77, 391-401)."""
+    psill = sill - nugget
+    if not (np.isfinite(psill) and np.isfinite(nugget)) or psill < 0 or nugget < 0:
+        return None
+    w = npairs / (dist * dist)
+
+    def sse(r):
+        e = gamma - (nugget + psill * (1.0 - np.exp(-dist / r)))
+        return float(np.sum(w * e * e))
+    r = 0.1 * float(np.max(dist))
+    if not (r > 0):
+        return None
+    s_old = sse(r)
+    gstat_done = False
+    for it in range(FIT_MAXIT + 60):
+        ex = np.exp(-dist / r)
+        e = gamma - (nugget + psill * (1.0 - ex))
+        J = -psill * ex * dist / (r * r)                    # d gamma_model / d range
+        den = float(np.sum(w * J * J))
+        if not (den > 0):
+            return None                                    # singular fit: gstat stops with an error
+        step = float(np.sum(w * J * e)) / den
+        s_new = None
+        for _h in range(12):
+            rn = r + step
+            if rn > 0:
+                s_new = sse(rn)
+                if s_new <= s_old:
+                    break
+            step *= 0.5
+            s_new = None
+        if s_new is None:
+            break                                          # no improving step: converged at r
+        small_step = abs(rn - r) <= 1e-10 * rn
+        r = rn
+        # gstat stops at a relative SSE change below fit_limit (or after 200 iterations); the iteration is continued to
+        # the minimiser itself so that the result does not depend on where inside that tolerance band one stops
+        if abs(s_old - s_new) <= FIT_LIMIT * max(s_new, 1e-300):
+            gstat_done = True
+        s_old = s_new
+        if small_step or (it >= FIT_MAXIT and gstat_done):
+            break
+    if not (np.isfinite(r) and r > 0):
+        return None
+    if nugget == 0 and psill == 0:                         # interp.R:74-77
+        return None
+    return nugget, psill, r
+
+
+def _ols_resid(X, y):
+    beta = np.linalg.solve(X.T @ X, X.T @ y)
+    return y - X @ beta
+
+
+def get_vario_params(ngh_lon, ngh_lat, ngh_X, ngh_y, ngh_dist):
+    """R ``get_vario_params`` (interp.R:54-113): exponential variogram (nugget, psill, range) of the regression-kriging
+    residuals of one neighbourhood.  ``ngh_X`` n x 4 (lon, lat, elev, lst), ``ngh_dist`` the haversine distances of the
+    neighbours from the point (StationSelect.ngh_dists).  Pure nugget -> (sill, 0, 0)."""
+    n = ngh_lon.size
+    H = gcdist_sp(ngh_lon[:, None], ngh_lat[:, None], ngh_lon[None, :], ngh_lat[None, :])
+    cutoff = float(np.max(ngh_dist)) * 1.4                                    # :63
+    k0 = int(np.argmin(ngh_dist))                                             # centre on the nearest neighbour (exact)
+    Xc = np.asarray(ngh_X, dtype=np.float64) - np.asarray(ngh_X, dtype=np.float64)[k0][None, :]
+    X = np.column_stack((np.ones(n), Xc[:, 0], Xc[:, 1], Xc[:, 2] * 1e-3, Xc[:, 3] * 0.1))
+    r = _ols_resid(X, ngh_y)                                                  # variogram(FORMULA, ...) works on OLS residuals
+    npairs, dist, gamma = sample_variogram(H, r, cutoff)                      # :64
+    sill = float(np.var(r, ddof=1))                                           # :66
+    model = fit_exp_range(npairs, dist, gamma, float(np.min(gamma)), sill) if gamma.size else None      # :68
+    # GLS trend with the fitted model, residuals at the stations (:79-81): predict(g, stns_ngh, BLUE=TRUE)
+    if model is None:
+        resid = r                                                             # V = sill I: GLS = OLS
+    else:
+        nug, psill, rng = model
+        V = np.where(H == 0, nug + psill, psill * np.exp(-H / rng))
+        V[np.diag_indices(n)] = nug + psill
+        Lc = np.linalg.cholesky(V)
+        Z = np.linalg.solve(Lc, np.column_stack((X, ngh_y)))
+        A, b = Z[:, :-1], Z[:, -1]
+        beta = np.linalg.solve(A.T @ A, A.T @ b)
+        resid = ngh_y - X @ beta
+    sill2 = float(np.var(resid, ddof=1))                                      # :82
+    npairs, dist, gamma = sample_variogram(H, resid, cutoff)                  # :83  variogram(resid~1)
+    model2 = fit_exp_range(npairs, dist, gamma, float(np.min(gamma)), sill2) if gamma.size else None    # :84
+    if model2 is None:
+        return sill2, 0.0, 0.0                                                # :86-93,103-107
+    return model2
+
+
+class BuildKrigParams(object):
+    """interp_tair.py:612-698: variogram parameters of a point and month with the smoothed optimal neighbour count."""
+
+    def __init__(self, stn_slct):
+        self.stn_slct = stn_slct
+
+    def get_krig_params(self, pt, mth, rm_stnid=None, nnghs=None):
+        ss = self.stn_slct
+        if nnghs is None:                                                      # :666-678
+            ss.set_ngh_stns(pt[LAT], pt[LON], DFLT_INIT_NNGHS, load_obs=False)
+            fin = np.isfinite(ss.ngh_stns[optim_name(mth)])
+            if fin.sum() == 0:
+                raise OracleError(ST_NO_NNGHS, "Cannot determine the optimal # of neighbors to use!")
+            nnghs = int(np.round(np.average(ss.ngh_stns[optim_name(mth)][fin], weights=ss.ngh_wgt[fin])))
+        ss.set_ngh_stns(pt[LAT], pt[LON], nnghs, load_obs=False, stns_rm=rm_stnid)    # :681 (rm_stnid unused there)
+        nghs = ss.ngh_stns
+        X = np.column_stack([nghs[LON], nghs[LAT], nghs[ELEV], nghs[lst_name(mth)]])
+        return get_vario_params(nghs[LON], nghs[LAT], X, nghs[norm_name(mth)], ss.ngh_dists)
+
+
+class KrigTairAll(object):
+    """interp_tair.py:700-768 + R krig_all (interp.R:147-159): variogram fit and regression kriging in one step."""
+
+    def __init__(self, stn_slct):
+        self.stn_slct = stn_slct
+
+    def krigall(self, pt, nnghs, stns_rm=None):
+        ss = self.stn_slct
+        ss.set_ngh_stns(pt[LAT], pt[LON], nnghs, load_obs=False, stns_rm=stns_rm)
+        nghs = ss.ngh_stns
+        interp_norms = np.zeros(12)
+        self.last_vario = np.zeros((12, 3))
+        for mth in range(1, 13):
+            X = np.column_stack([nghs[LON], nghs[LAT], nghs[ELEV], nghs[lst_name(mth)]])
+            y = nghs[norm_name(mth)]
+            nug, psill, rng = get_vario_params(nghs[LON], nghs[LAT], X, y, ss.ngh_dists)
+            x = np.array([pt[LON], pt[LAT], pt[ELEV], pt[lst_name(mth)]], dtype=np.float64)
+            mean, var = ked_gstat(nghs[LON], nghs[LAT], X, y, pt[LON], pt[LAT], x, nug, psill, rng)
+            interp_norms[mth - 1] = mean
+            self.last_vario[mth - 1] = (nug, psill, rng)
+        return interp_norms
+
+
+class XvalTairNorm(object):
+    """optimize.py:210-266: leave-one-out error of the kriged normals for a set of neighbour counts."""
+
+    def __init__(self, stn_da):
+        mask_stns = np.isnan(stn_da.stns[BAD])
+        ss = StationSelect(stn_da, stn_mask=mask_stns, rm_zero_dist_stns=True)
+        self.krig = KrigTairAll(ss)
+        self.stn_da = stn_da
+
+    def run_xval(self, stn_id, abw_nngh):
+        xval_stn = self.stn_da.stns[self.stn_da.stn_idxs[stn_id]]
+        err = np.zeros((12, len(abw_nngh)))
+        xval_norms = np.array([xval_stn[norm_name(m)] for m in range(1, 13)])
+        for x, bw in enumerate(abw_nngh):
+            err[:, x] = self.krig.krigall(xval_stn, int(bw), stns_rm=stn_id) - xval_norms
+        return err

@@ -51,6 +51,9 @@ def build():
         elev = float(f.elev(lon, lat))
         tdi = float(f.tdi(lon, lat))
         lst = float(f.lst(1, mth, lon, lat, elev))
+        if kind == "at_station":                                # same predictors as the station: x0 = x_k, so the
+            kk = int(np.argmin(o.gcdist_sp(lon, lat, nghs[o.LON], nghs[o.LAT])))     # predictor is exact there
+            elev, tdi, lst = float(nghs[o.ELEV][kk]), float(nghs[o.TDI][kk]), float(nghs[o.lst_name(mth)][kk])
         nug, psill, vr = rng.uniform(0.05, 0.5), rng.uniform(0.2, 3.0), rng.uniform(20.0, 300.0)
         if ci in (7, 23, 39, 55):                               # pure nugget branch
             kind, nug, psill, vr = "nugget", nug + psill, 0.0, 0.0

@@ -138,3 +138,53 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["unit"] == "cell-days/s" and d["higher_is_better"] is True
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["value"] > 0
+
+
+def test_tile_writer_roundtrip(tmp_path):
+    """TileWriter (tiling.py:304-537): variables, dtypes, fill values, scale factor; chunk-wise and whole-tile writes agree."""
+    from scipy.io import netcdf_file
+    from topowx_b200 import synth
+    from topowx_b200.interp.tiling import Tiler, TileWriter, AsyncTileWriter
+    ny, nx = 20, 30
+    mask = np.ones((ny, nx), dtype=bool)
+    lats, lons = synth.grid_lats(np.arange(ny)), synth.grid_lons(np.arange(nx))
+    t = Tiler(dict(mask=mask, lon=lons, lat=lats), [], 10, 10, 5, 5)
+    info = t.build_tile_grid_info()
+    days = synth.make_days(1995, 1)[:40]
+    rng = np.random.default_rng(3)
+    tile = dict(tmin=rng.integers(-3000, 3000, (40, 10, 10)).astype(np.int16), tmax=rng.integers(-3000, 3000, (40, 10, 10)).astype(np.int16),
+                tmin_norm=rng.normal(size=(12, 10, 10)).astype(np.float32), tmax_norm=rng.normal(size=(12, 10, 10)).astype(np.float32),
+                tmin_se=rng.uniform(size=(12, 10, 10)).astype(np.float32), tmax_se=rng.uniform(size=(12, 10, 10)).astype(np.float32),
+                ninvalid=rng.integers(0, 5, (10, 10)).astype(np.int32), status=np.zeros((10, 10), np.uint8))
+    tw = TileWriter(info, str(tmp_path / "a"))
+    os.makedirs(str(tmp_path / "a"))
+    tid = info.get_tile_id(1)
+    # chunk by chunk, like the writer rank of step25 (step25:229-249); one chunk is left unwritten -> fill values
+    for y in range(0, 10, 5):
+        for x in range(0, 10, 5):
+            if (y, x) == (5, 5):
+                continue
+            tw.write_tile_chunk(tid, "tmin", days, y, x, tile["tmin"][:, y:y + 5, x:x + 5], tile["tmin_norm"][:, y:y + 5, x:x + 5],
+                                tile["tmin_se"][:, y:y + 5, x:x + 5], tile["ninvalid"][y:y + 5, x:x + 5])
+    if tw.format.startswith("netCDF3"):
+        ds = netcdf_file(os.path.join(str(tmp_path / "a"), tid, "%s_tmin.nc" % tid), "r", mmap=False, maskandscale=False)
+        v = ds.variables["tmin"]
+        assert v.data.dtype.kind == "i" and v.data.dtype.itemsize == 2 and v.data.shape == (40, 10, 10)
+        assert np.array_equal(v.data[:, :5, :], tile["tmin"][:, :5, :]) and (v.data[:, 5:, 5:] == -32767).all()
+        assert abs(float(v.scale_factor) - 0.01) < 1e-9 and int(v._FillValue) == -32767
+        assert np.array_equal(ds.variables["tmin_normal"].data[:, :5, :5], tile["tmin_norm"][:, :5, :5])
+        assert (ds.variables["inconsist_tair"].data[5:, 5:] == -2147483647).all()
+        assert ds.variables["time"].data.shape == (40,) and ds.variables["time"].data[0] == 0.5
+        r0, c0 = info.tile_rc[tid]
+        assert np.allclose(ds.variables["lat"].data, lats[r0:r0 + 10]) and np.allclose(ds.variables["lon"].data, lons[c0:c0 + 10])
+        assert ds.variables["climatology_bounds"].data.shape == (12, 2)
+        ds.close()
+    # whole tiles through the background writer, netCDF and raw
+    for fmt in ("nc", "raw"):
+        aw = AsyncTileWriter(info, str(tmp_path / fmt), days, fmt=fmt)
+        aw.submit(tid, tile)
+        nbytes = aw.wait()
+        aw.close()
+        assert nbytes > tile["tmin"].nbytes * 2
+    raw = np.load(os.path.join(str(tmp_path / "raw"), tid, "%s_tmax.npy" % tid))
+    assert np.array_equal(raw, tile["tmax"])

@@ -57,13 +57,17 @@ def _load():
         "twxi_ctx_set_climdivs": (i32, [vp, vp, i32]),
         "twxi_ctx_set_stream": (i32, [vp, vp]),
         "twxi_ctx_destroy": (i32, [vp]),
+        "twxi_ctx_stat": (i32, [vp, i32, vp]),
         "twxi_ctx_n_stns": (i32, [vp]),
         "twxi_ctx_n_days": (i32, [vp]),
         "twxi_knn": (i32, [vp, i32, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, i32]),
         "twxi_nngh_params": (i32, [vp, C.POINTER(Points), vp, vp, vp, vp, i32]),
         "twxi_krig": (i32, [vp, C.POINTER(Points), i32, vp, vp, vp, vp, vp, i32]),
+        "twxi_fit_vario": (i32, [vp, C.POINTER(Points), i32, vp, vp, vp, i32]),
+        "twxi_krig_all": (i32, [vp, C.POINTER(Points), vp, vp, vp, vp, vp, i32]),
         "twxi_gwr_hat": (i32, [vp, C.POINTER(Points), i32, vp, i32, vp, vp, vp, vp, i32]),
         "twxi_gwr_mth": (i32, [vp, C.POINTER(Points), i32, vp, vp, vp, vp, i32]),
+        "twxi_xval_anom": (i32, [vp, i32, vp, i32, vp, vp, vp, vp, vp, i32]),
         "twxi_interp_points": (i32, [vp, C.POINTER(Points), vp, vp, vp, vp, vp, i32]),
         "twxi_interp_cells": (i32, [vp, vp, i32] + [vp] * 9 + [i32, i32, i32] + [vp] * 8 + [i32]),
         "twxi_interp_chunk": (i32, [vp, vp, vp, i32, i32] + [vp] * 8 + [i32]),

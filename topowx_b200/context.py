@@ -139,6 +139,27 @@ class TwxiContext(object):
         check(lib.twxi_krig(self._h, C.byref(p), int(mth), ptr(nn), ptr(vo), ptr(mean), ptr(var), ptr(st), MEM_HOST))
         return mean, var, st
 
+    def fit_vario(self, lat, lon, mth=0, nnghs=None, rm_idx=None, rm_zero=False):
+        """twxi_fit_vario: (nugget, psill, range) [n, 12 or 1, 3] of the neighbourhoods of the points, status [n]."""
+        p, keep = self._points(lat, lon, rm_idx=rm_idx, rm_zero=rm_zero)
+        n, nm = p.npts, (1 if mth else 12)
+        vario = np.empty((n, nm, 3))
+        st = np.empty(n, dtype=np.uint8)
+        nn = None if nnghs is None else np.ascontiguousarray(np.broadcast_to(nnghs, (n,)), dtype=np.int32)
+        check(lib.twxi_fit_vario(self._h, C.byref(p), int(mth), ptr(nn), ptr(vario), ptr(st), MEM_HOST))
+        return vario, st
+
+    def krig_all(self, lat, lon, elev, lst, nnghs, rm_idx=None, rm_zero=False):
+        """twxi_krig_all: variogram fit + kriging of all 12 months with ``nnghs`` neighbours per point.
+        Returns mean, var [n, 12], vario [n, 12, 3], status [n]."""
+        p, keep = self._points(lat, lon, elev=elev, lst=lst, rm_idx=rm_idx, rm_zero=rm_zero)
+        n = p.npts
+        mean, var, vario = np.empty((n, 12)), np.empty((n, 12)), np.empty((n, 12, 3))
+        st = np.empty(n, dtype=np.uint8)
+        nn = np.ascontiguousarray(np.broadcast_to(nnghs, (n,)), dtype=np.int32)
+        check(lib.twxi_krig_all(self._h, C.byref(p), ptr(nn), ptr(mean), ptr(var), ptr(vario), ptr(st), MEM_HOST))
+        return mean, var, vario, st
+
     def gwr_hat(self, lat, lon, elev, tdi, lst, mth, nnghs=None, rm_idx=None, rm_zero=False, kmax=_lib.MAX_NNGHS):
         p, keep = self._points(lat, lon, elev=elev, tdi=tdi, lst=lst, rm_idx=rm_idx, rm_zero=rm_zero)
         n = p.npts
@@ -160,6 +181,17 @@ class TwxiContext(object):
         nn = None if nnghs is None else np.ascontiguousarray(np.broadcast_to(nnghs, (n,)), dtype=np.int32)
         check(lib.twxi_gwr_mth(self._h, C.byref(p), int(mth), ptr(nn), ptr(ptn), ptr(out), ptr(st), MEM_HOST))
         return out, st
+
+    def xval_anom(self, stn_idx, nnghs):
+        """twxi_xval_anom: leave-one-out GWR at the stations ``stn_idx`` (context indices) for every neighbour count of
+        ``nnghs``.  Returns bias, mae, r2 [n, len(nnghs), 12] and status [n]."""
+        stn_idx = np.ascontiguousarray(stn_idx, dtype=np.int32)
+        nnghs = np.ascontiguousarray(nnghs, dtype=np.int32)
+        n, nc = stn_idx.size, nnghs.size
+        bias, mae, r2 = (np.empty((n, nc, 12)) for _ in range(3))
+        st = np.empty(n, dtype=np.uint8)
+        check(lib.twxi_xval_anom(self._h, n, ptr(stn_idx), nc, ptr(nnghs), ptr(bias), ptr(mae), ptr(r2), ptr(st), MEM_HOST))
+        return bias, mae, r2, st
 
     def interp_points(self, lat, lon, elev, tdi, lst, rm_idx=None, rm_zero=False, daily=True):
         p, keep = self._points(lat, lon, elev=elev, tdi=tdi, lst=lst, rm_idx=rm_idx, rm_zero=rm_zero)

@@ -340,6 +340,14 @@ int twxi_ctx_destroy(twxi_ctx* c) {
     return TWXI_OK;
 }
 
+int twxi_ctx_stat(twxi_ctx* c, int which, double* out) {
+    TWXI_ARG(c && out, "null argument");
+    TWXI_CUDA(cudaSetDevice(c->device));
+    if (which == 0) return knn_mean_candidates(*c, out);
+    set_error("unknown statistic");
+    return TWXI_ERR_ARG;
+}
+
 int twxi_ctx_n_stns(const twxi_ctx* c) { return c ? c->n : 0; }
 int twxi_ctx_n_days(const twxi_ctx* c) { return (c && c->has_obs) ? c->ob.ndays : 0; }
 
@@ -520,6 +528,67 @@ int twxi_krig(twxi_ctx* c, const twxi_points* pts, int mth, const int32_t* nnghs
     return finish(*c, mem);
 }
 
+// vario [npts][12][3] -> caller's [npts][12|1][3] with NaN for failed points (and for months that were not requested)
+static int copy_vario(Ctx& c, int npts, int mth, double* out) {
+    const int nm = mth ? 1 : 12;
+    double* tmp;
+    TWXI_TRY(c.scratch[0].get((void**)&tmp, (size_t)npts * nm * 3 * 8));
+    TWXI_TRY(launch_gather_vario(c.stream, npts, mth - 1, c.b.status, c.b.nn, c.b.vario, tmp));
+    return copy_out(c, out, tmp, (size_t)npts * nm * 3);
+}
+
+int twxi_fit_vario(twxi_ctx* c, const twxi_points* pts, int mth, const int32_t* nnghs_override, double* vario,
+                   uint8_t* status, int mem) {
+    TWXI_ARG(c && pts && vario && status, "null argument");
+    TWXI_ARG(mth >= 0 && mth <= 12, "mth must be 0..12");
+    TWXI_CUDA(cudaSetDevice(c->device));
+    const int npts = pts->npts;
+    TWXI_TRY(load_points(*c, pts, k1_for_override(*c, nnghs_override, npts, mem, nnghs_override == nullptr), false));
+    if (npts == 0) return TWXI_OK;
+    Batch& b = c->b;
+    const int32_t* d_ovr;
+    TWXI_TRY(upload_override(*c, nnghs_override, npts, 2, &d_ovr));
+    TWXI_TRY(run_knn(*c));
+    TWXI_TRY(launch_nngh_params(*c, b, d_ovr, nullptr, mth, 1, 0, 0));
+    TWXI_TRY(launch_vario_fit(*c, b, mth));
+    uint8_t* st8;
+    TWXI_TRY(c->scratch[1].get((void**)&st8, npts));
+    TWXI_TRY(launch_status_to_u8(c->stream, npts, b.status, st8));
+    TWXI_TRY(copy_vario(*c, npts, mth, vario));
+    TWXI_TRY(copy_out(*c, status, st8, (size_t)npts));
+    return finish(*c, mem);
+}
+
+int twxi_krig_all(twxi_ctx* c, const twxi_points* pts, const int32_t* nnghs, double* mean, double* var, double* vario,
+                  uint8_t* status, int mem) {
+    TWXI_ARG(c && pts && nnghs && mean && status, "null argument");
+    TWXI_ARG(pts->elev && pts->lst, "elev and lst are required for kriging");
+    TWXI_CUDA(cudaSetDevice(c->device));
+    const int npts = pts->npts;
+    TWXI_TRY(load_points(*c, pts, k1_for_override(*c, nnghs, npts, mem, false), false));
+    if (npts == 0) return TWXI_OK;
+    Batch& b = c->b;
+    const int32_t* d_ovr;
+    TWXI_TRY(upload_override(*c, nnghs, npts, 2, &d_ovr));
+    TWXI_TRY(run_knn(*c));
+    TWXI_TRY(launch_nngh_params(*c, b, d_ovr, nullptr, 0, 1, 0, 0));
+    TWXI_TRY(launch_vario_fit(*c, b, 0));
+    TWXI_TRY(launch_krig(*c, b, 0, nullptr));
+    uint8_t* st8;
+    double* tmp;
+    const size_t cnt = (size_t)npts * 12;
+    TWXI_TRY(c->scratch[1].get((void**)&st8, npts));
+    TWXI_TRY(c->scratch[3].get((void**)&tmp, cnt * 16));
+    TWXI_TRY(launch_status_to_u8(c->stream, npts, b.status, st8));
+    TWXI_TRY(launch_gather_month(c->stream, npts, -1, b.status, b.mean, tmp));
+    TWXI_TRY(launch_gather_month(c->stream, npts, -1, b.status, b.var, tmp + cnt));
+    TWXI_TRY(copy_out(*c, mean, tmp, cnt));
+    TWXI_TRY(copy_out(*c, var, tmp + cnt, cnt));
+    if (vario) TWXI_TRY(copy_vario(*c, npts, 0, vario));
+    TWXI_TRY(copy_out(*c, status, st8, (size_t)npts));
+    return finish(*c, mem);
+}
+
 int twxi_gwr_hat(twxi_ctx* c, const twxi_points* pts, int mth, const int32_t* nnghs_override, int kmax, int32_t* k,
                  int32_t* idx, double* z, uint8_t* status, int mem) {
     TWXI_ARG(c && pts && k && idx && z && status, "null argument");
@@ -582,6 +651,43 @@ int twxi_gwr_mth(twxi_ctx* c, const twxi_points* pts, int mth, const int32_t* nn
     TWXI_TRY(c->scratch[1].get((void**)&st8, npts));
     TWXI_TRY(launch_status_to_u8(c->stream, npts, b.status, st8));
     TWXI_TRY(copy_out(*c, out, d_out, (size_t)npts * D));
+    TWXI_TRY(copy_out(*c, status, st8, (size_t)npts));
+    return finish(*c, mem);
+}
+
+int twxi_xval_anom(twxi_ctx* c, int npts, const int32_t* stn_idx, int n_counts, const int32_t* nnghs, double* bias,
+                   double* mae, double* r2, uint8_t* status, int mem) {
+    TWXI_ARG(c && stn_idx && nnghs && bias && mae && r2 && status, "null argument");
+    TWXI_ARG(npts >= 0 && n_counts >= 1 && n_counts <= 64, "bad sizes");
+    if (!c->has_obs) { set_error("twxi_ctx_set_obs has not been called"); return TWXI_ERR_STATE; }
+    TWXI_CUDA(cudaSetDevice(c->device));
+    if (npts == 0) return TWXI_OK;
+    int kmax = 0;
+    for (int i = 0; i < n_counts; ++i) {
+        TWXI_ARG(nnghs[i] >= 6 && nnghs[i] <= TWXI_MAX_NNGHS, "neighbour count out of range (6..TWXI_MAX_NNGHS)");
+        kmax = std::max(kmax, (int)nnghs[i]);
+    }
+    TWXI_TRY(ensure_batch(*c, npts, kmax + 1, false));
+    Batch& b = c->b;
+    b.n_rm = 1; b.rm_zero = 1; b.gy = b.gx = 0;                // optimize.py:499: rm_zero_dist_stns=True, stns_rm = the station
+    int32_t* d_idx;
+    TWXI_TRY(c->scratch[2].get((void**)&d_idx, (size_t)npts * 4));
+    TWXI_CUDA(cudaMemcpyAsync(d_idx, stn_idx, (size_t)npts * 4, cudaMemcpyDefault, c->stream));
+    TWXI_TRY(launch_station_points(*c, b, npts, d_idx));
+    TWXI_TRY(run_knn(*c));
+    const size_t cnt = (size_t)npts * n_counts * 12;
+    double* d_out;
+    TWXI_TRY(c->scratch[0].get((void**)&d_out, cnt * 3 * 8 + cnt * 3 * 8));
+    TWXI_CUDA(cudaMemsetAsync(d_out, 0xff, cnt * 3 * 8, c->stream));       // NaN where a system is not computed
+    TWXI_TRY(launch_gwr_xval(*c, b, d_idx, nnghs, n_counts, d_out));
+    double* d_split = d_out + cnt * 3;
+    TWXI_TRY(launch_split3(c->stream, cnt, d_out, b.status, n_counts * 12, d_split, d_split + cnt, d_split + 2 * cnt));
+    uint8_t* st8;
+    TWXI_TRY(c->scratch[1].get((void**)&st8, npts));
+    TWXI_TRY(launch_status_to_u8(c->stream, npts, b.status, st8));
+    TWXI_TRY(copy_out(*c, bias, d_split, cnt));
+    TWXI_TRY(copy_out(*c, mae, d_split + cnt, cnt));
+    TWXI_TRY(copy_out(*c, r2, d_split + 2 * cnt, cnt));
     TWXI_TRY(copy_out(*c, status, st8, (size_t)npts));
     return finish(*c, mem);
 }

@@ -280,4 +280,23 @@ int launch_gather_month(cudaStream_t s, int npts, int mth0, const int32_t* st, c
     return TWXI_OK;
 }
 
+// variogram parameters [npts][12][3] -> [npts][12|1][3], NaN for failed points / months without a system
+__global__ void gather_vario_kernel(int npts, int mth0, const int32_t* st, const int32_t* nn, const double* src, double* dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nm = mth0 >= 0 ? 1 : 12;
+    if (i >= npts * nm) return;
+    const int q = i / nm, m = mth0 >= 0 ? mth0 : i % nm;
+    const bool good = st[q] == TWXI_ST_OK && nn[(size_t)q * 24 + m] > 0;
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    for (int k = 0; k < 3; ++k) dst[(size_t)i * 3 + k] = good ? src[((size_t)q * 12 + m) * 3 + k] : nan;
+}
+int launch_gather_vario(cudaStream_t s, int npts, int mth0, const int32_t* st, const int32_t* nn, const double* src,
+                        double* dst) {
+    if (npts <= 0) return TWXI_OK;
+    const int n = npts * (mth0 >= 0 ? 1 : 12);
+    gather_vario_kernel<<<(n + 255) / 256, 256, 0, s>>>(npts, mth0, st, nn, src, dst);
+    TWXI_LAUNCH_CHECK();
+    return TWXI_OK;
+}
+
 }  // namespace twxi

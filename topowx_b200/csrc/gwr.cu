@@ -37,6 +37,13 @@ struct GwrArgs {
     int32_t* hat_idx;
     double* hat_z;
     int32_t* status;
+    // cross validation of the neighbour count (XvalTairAnom.run_xval, optimize.py:505-545): every point is a station of the
+    // table (xv_self, left out by the neighbour search), k is fixed, and instead of daily values the kernel returns
+    // bias / MAE / r^2 of the interpolated against the station's own anomalies
+    int k_fixed;               // > 0: neighbour count of every point (nn is not read)
+    const int32_t* xv_self;    // [npts] station index of the point, or null
+    double* xv_out;            // [npts][xv_nc][12][3]
+    int xv_nc, xv_ci;
 };
 
 __global__ void __launch_bounds__(GWR_THREADS, 4) gwr_kernel(GwrArgs a) {
@@ -51,7 +58,7 @@ __global__ void __launch_bounds__(GWR_THREADS, 4) gwr_kernel(GwrArgs a) {
     const int q = (int)(item % a.npts);
     const int m = a.single_mth >= 0 ? a.single_mth : (int)(item / a.npts);
     if (a.status[q] != TWXI_ST_OK) return;
-    const int k = a.nn[(size_t)q * 24 + 12 + m];
+    const int k = a.k_fixed > 0 ? a.k_fixed : a.nn[(size_t)q * 24 + 12 + m];
     if (k < 1) return;
     const int N = a.st.n;
     const int32_t* idx = a.idx + (size_t)q * a.k1;
@@ -143,12 +150,14 @@ __global__ void __launch_bounds__(GWR_THREADS, 4) gwr_kernel(GwrArgs a) {
     zn = warp_sum(zn);
     if (a.hat_k && lane == 0) a.hat_k[q] = k;
     __syncwarp();
-    if (!a.daily && !a.out_month) return;
+    if (!a.daily && !a.out_month && !a.xv_out) return;
 
     // ---- daily values: lanes = days of the month, neighbours gathered from the station-major obs table ------------
-    const double ptn = a.pt_norm_single ? a.pt_norm[q] : a.pt_norm[(size_t)q * 12 + m];
+    const int self = a.xv_self ? a.xv_self[q] : 0;
+    const double ptn = a.xv_self ? normm[self] : (a.pt_norm_single ? a.pt_norm[q] : a.pt_norm[(size_t)q * 12 + m]);
     const double off = ptn - zn;
     const int p0 = a.ob.moff[m], D = a.ob.moff[m + 1] - p0;
+    double sd = 0.0, sad = 0.0, sx = 0.0, sy = 0.0, sxx = 0.0, syy = 0.0, sxy = 0.0;    // xval sums over the days of this lane
     for (int d0 = 0; d0 < D; d0 += 32) {
         const int d = d0 + lane;
         const bool valid = d < D;
@@ -170,14 +179,59 @@ __global__ void __launch_bounds__(GWR_THREADS, 4) gwr_kernel(GwrArgs a) {
         if (valid) {
             if (a.daily) a.daily[(size_t)q * nd + a.ob.day_of_pos[p0 + d]] = v;
             if (a.out_month) a.out_month[(size_t)q * D + d] = v;
+            if (a.xv_out) {                                   // optimize.py:520-531
+                const double x = v - ptn;                                        // interpolated anomaly
+                const double y = (double)a.ob.obsT[(size_t)self * nd + p0 + d] - ptn;    // the station's own anomaly
+                const double dif = x - y;
+                sd += dif; sad += fabs(dif); sx += x; sy += y; sxx += x * x; syy += y * y; sxy += x * y;
+            }
         }
     }
+    if (a.xv_out) {
+        sd = warp_sum(sd); sad = warp_sum(sad); sx = warp_sum(sx); sy = warp_sum(sy);
+        sxx = warp_sum(sxx); syy = warp_sum(syy); sxy = warp_sum(sxy);
+        if (lane == 0) {
+            const double n = (double)D;
+            const double cxy = sxy - sx * sy / n, cxx = sxx - sx * sx / n, cyy = syy - sy * sy / n;
+            const double r = cxy / sqrt(cxx * cyy);           // = scipy.stats.linregress(x, y)[2]
+            double* o = a.xv_out + (((size_t)q * a.xv_nc + a.xv_ci) * 12 + m) * 3;
+            o[0] = sd / n; o[1] = sad / n; o[2] = r * r;
+        }
+    }
+}
+
+static void gwr_fill(GwrArgs& a, Ctx& c, Batch& b, int mth);
+
+// XvalTairAnom: one launch per neighbour count over (point, month) items; the neighbour search has run once with the
+// largest count
+int launch_gwr_xval(Ctx& c, Batch& b, const int32_t* self, const int32_t* counts_host, int ncounts, double* out) {
+    if (b.npts <= 0) return TWXI_OK;
+    GwrArgs a;
+    gwr_fill(a, c, b, 0);
+    a.xv_self = self; a.xv_out = out; a.xv_nc = ncounts;
+    const long long items = (long long)b.npts * 12;
+    for (int i = 0; i < ncounts; ++i) {
+        a.k_fixed = counts_host[i]; a.xv_ci = i;
+        gwr_kernel<<<(unsigned)((items + GWR_WARPS - 1) / GWR_WARPS), GWR_THREADS, 0, c.stream>>>(a);
+        TWXI_LAUNCH_CHECK();
+    }
+    return TWXI_OK;
+}
+
+static void gwr_fill(GwrArgs& a, Ctx& c, Batch& b, int mth) {
+    a.st = c.st; a.ob = c.ob; a.npts = b.npts; a.k1 = b.k1; a.single_mth = mth >= 1 ? mth - 1 : -1;
+    a.idx = b.idx; a.dist = b.dist; a.nn = b.nn;
+    a.qlon = b.lon; a.qlat = b.lat; a.qelev = b.elev; a.qtdi = b.tdi; a.qlst = b.lst;
+    a.pt_norm = b.mean; a.pt_norm_single = 0; a.daily = nullptr; a.out_month = nullptr;
+    a.kmax = 0; a.hat_k = nullptr; a.hat_idx = nullptr; a.hat_z = nullptr; a.status = b.status;
+    a.k_fixed = 0; a.xv_self = nullptr; a.xv_out = nullptr; a.xv_nc = 0; a.xv_ci = 0;
 }
 
 int launch_gwr(Ctx& c, Batch& b, int mth, const double* pt_norm_override, int write_daily, double* out_month,
                int kmax, int32_t* hat_k, int32_t* hat_idx, double* hat_z) {
     if (b.npts <= 0) return TWXI_OK;
     GwrArgs a;
+    gwr_fill(a, c, b, mth);
     a.st = c.st; a.ob = c.ob; a.npts = b.npts; a.k1 = b.k1; a.single_mth = mth >= 1 ? mth - 1 : -1;
     a.idx = b.idx; a.dist = b.dist; a.nn = b.nn;
     a.qlon = b.lon; a.qlat = b.lat; a.qelev = b.elev; a.qtdi = b.tdi; a.qlst = b.lst;
@@ -189,6 +243,47 @@ int launch_gwr(Ctx& c, Batch& b, int mth, const double* pt_norm_override, int wr
     a.status = b.status;
     const long long items = (long long)b.npts * (mth >= 1 ? 1 : 12);
     gwr_kernel<<<(unsigned)((items + GWR_WARPS - 1) / GWR_WARPS), GWR_THREADS, 0, c.stream>>>(a);
+    TWXI_LAUNCH_CHECK();
+    return TWXI_OK;
+}
+
+}  // namespace twxi
+
+namespace twxi {
+
+// Points of a cross validation are stations of the table itself (the reference passes the station record as `pt`,
+// optimize.py:517,590): gather their coordinates / predictors and leave each one out of its own neighbour search.
+__global__ void station_points_kernel(StnTable st, int npts, const int32_t* sidx, Batch b) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= npts) return;
+    const int s = sidx[q];
+    const bool ok = s >= 0 && s < st.n;
+    const int t = ok ? s : 0;
+    b.lat[q] = st.lat[t]; b.lon[q] = st.lon[t]; b.elev[q] = st.elev[t]; b.tdi[q] = st.tdi[t];
+    for (int m = 0; m < 12; ++m) b.lst[(size_t)q * 12 + m] = st.lst[(size_t)m * st.n + t];
+    b.rm_idx[q] = ok ? s : -1;
+    b.status[q] = ok ? TWXI_ST_OK : TWXI_ST_TOO_FEW_STNS;
+}
+int launch_station_points(Ctx& c, Batch& b, int npts, const int32_t* sidx) {
+    if (npts <= 0) return TWXI_OK;
+    station_points_kernel<<<(npts + 255) / 256, 256, 0, c.stream>>>(c.st, npts, sidx, b);
+    TWXI_LAUNCH_CHECK();
+    return TWXI_OK;
+}
+
+__global__ void split3_kernel(size_t n, const double* src, const int32_t* status, int per_point, double* a, double* b, double* c) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool good = status[i / per_point] == TWXI_ST_OK;
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    a[i] = good ? src[3 * i] : nan;
+    b[i] = good ? src[3 * i + 1] : nan;
+    c[i] = good ? src[3 * i + 2] : nan;
+}
+int launch_split3(cudaStream_t s, size_t n, const double* src, const int32_t* status, int per_point, double* a, double* b,
+                  double* c) {
+    if (n == 0) return TWXI_OK;
+    split3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, src, status, per_point, a, b, c);
     TWXI_LAUNCH_CHECK();
     return TWXI_OK;
 }

@@ -88,6 +88,11 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(KnnArgs a) {
         if (cnt >= 0) { cand = a.cand + (size_t)b * a.cand_cap; n = cnt; }
     }
 
+    if (n < k1) {                                              // fewer stations than candidates wanted: IndexError at
+        if (tid == 0) a.status[q] = TWXI_ST_TOO_FEW_STNS;      // station_select.py:164 (the select below needs n >= k1)
+        return;
+    }
+
     // ---- phase 1: haversine "a" of every station (util_geo.py:27-36) -------------------------------
     const double lat1rad = __dmul_rn(a.qlat[q], TWX_RAD);
     const double lon1rad = __dmul_rn(a.qlon[q], TWX_RAD);
@@ -326,11 +331,26 @@ int launch_build_dist_table(cudaStream_t s, int n, const double* lon, const doub
     return TWXI_OK;
 }
 
-struct KnnWork {                 // candidate lists of the gridded search, owned per thread
+struct KnnWork {                 // candidate lists of the gridded search, owned by the context
     int32_t* cand = nullptr;
     int32_t* cnt = nullptr;
     size_t cand_elems = 0, cnt_elems = 0;
+    int last_blocks = 0;         // blocks of the most recent gridded search (instrumentation)
 };
+
+// mean length of the candidate lists of the most recent gridded search of this context (-1: none): twxi_ctx_stat(ctx, 0)
+int knn_mean_candidates(Ctx& c, double* out) {
+    *out = -1.0;
+    if (!c.knn || c.knn->last_blocks <= 0) return TWXI_OK;
+    std::vector<int32_t> h(c.knn->last_blocks);
+    TWXI_CUDA(cudaMemcpyAsync(h.data(), c.knn->cnt, h.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+    TWXI_CUDA(cudaStreamSynchronize(c.stream));
+    double s = 0;
+    int m = 0;
+    for (int v : h) if (v >= 0) { s += v; ++m; }
+    if (m) *out = s / m;
+    return TWXI_OK;
+}
 void knn_work_free(KnnWork* w) {
     if (!w) return;
     if (w->cand) cudaFree(w->cand);
@@ -372,6 +392,7 @@ int launch_knn(Ctx& c, int npts, const double* lat, const double* lon, const int
         knn_candidates_kernel<<<nby * nbx, KNN_THREADS, smem_c, c.stream>>>(a, gy, w.cand, w.cnt);
         TWXI_LAUNCH_CHECK();
         a.cand = w.cand; a.cand_cnt = w.cnt;
+        w.last_blocks = nby * nbx;
     }
     size_t smem = (size_t)c.n * 8 + KNN_SEL * 12 + 256 * 4;
     TWXI_CUDA(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -133,6 +133,8 @@ struct KedWork;                  // ked.cu: device scratch + launch configuratio
 struct KnnWork;                  // knn.cu: candidate lists of the gridded search
 void ked_work_free(KedWork*);
 void knn_work_free(KnnWork*);
+struct Ctx;
+int knn_mean_candidates(Ctx& c, double* out);
 
 struct Ctx {
     int device = 0;
@@ -160,8 +162,13 @@ int launch_knn(Ctx& c, int npts, const double* lat, const double* lon, const int
 int launch_nngh_params(Ctx& c, Batch& b, const int32_t* norm_override, const int32_t* anom_override, int only_mth,
                        int need_norm, int need_anom, int need_vario);
 int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override);
+int launch_vario_fit(Ctx& c, Batch& b, int mth);
 int launch_gwr(Ctx& c, Batch& b, int mth, const double* pt_norm_override, int write_daily,
                double* out_month, int kmax, int32_t* hat_k, int32_t* hat_idx, double* hat_z);
+int launch_gwr_xval(Ctx& c, Batch& b, const int32_t* self, const int32_t* counts_host, int ncounts, double* out);
+int launch_station_points(Ctx& c, Batch& b, int npts, const int32_t* sidx);
+int launch_split3(cudaStream_t s, size_t n, const double* src, const int32_t* status, int per_point, double* a, double* b,
+                  double* c);
 int launch_build_dist_table(cudaStream_t s, int n, const double* lon, const double* lat, double* H);
 int launch_station_trig(cudaStream_t s, int n, const double* lon, const double* lat, double* lonrad,
                         double* latrad, double* coslat);
@@ -177,6 +184,8 @@ int launch_finalize_points(Ctx& c, Batch& b, double* daily, double* norms, doubl
                            uint8_t* status);
 int launch_status_to_u8(cudaStream_t s, int n, const int32_t* in, uint8_t* out);
 int launch_gather_month(cudaStream_t s, int npts, int mth0, const int32_t* st, const double* src12, double* dst);
+int launch_gather_vario(cudaStream_t s, int npts, int mth0, const int32_t* st, const int32_t* nn, const double* src,
+                        double* dst);
 
 // ---- small device helpers -----------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {

@@ -9,7 +9,7 @@ BuildKrigParams (variogram fitting in R/gstat), PredictorGrids / interp_to_lonla
 GwrTairNorm.
 '''
 
-__all__ = ["GwrTairAnom", 'KrigTair', 'InterpTair', 'StationDataWrkChk', 'PtInterpTair']
+__all__ = ["GwrTairAnom", 'KrigTair', 'KrigTairAll', 'BuildKrigParams', 'InterpTair', 'StationDataWrkChk', 'PtInterpTair']
 
 import numpy as np
 
@@ -106,6 +106,50 @@ class KrigTair(object):
                                  vario=vario_params, rm_idx=ctx.rm_indices(stns_rm), rm_zero=ss.rm_zero_dist_stns)
         _raise_status(st[0])
         return float(mean[0, 0]), float(var[0, 0])
+
+
+class BuildKrigParams(object):
+    '''
+    Moving window regression kriging variogram parameters for a specific point (interp_tair.py:612-698): the R
+    function get_vario_params (gstat variogram + fit.variogram, interp.R:54-113) runs as a CUDA kernel (twxi_fit_vario).
+    '''
+
+    def __init__(self, stn_slct):
+        self.stn_slct = stn_slct
+
+    def get_krig_params(self, pt, mth, rm_stnid=None):
+        '''
+        Returns (nug, psill, rng) of the exponential variogram for month `mth` at `pt`, with the smoothed optimal
+        number of neighbours.  Like the reference (:681), `rm_stnid` is accepted but not applied to the neighbour search.
+        '''
+        ss = self.stn_slct
+        vario, st = ss.ctx.fit_vario(pt[LAT], pt[LON], mth=int(mth), rm_zero=ss.rm_zero_dist_stns)
+        _raise_status(st[0])
+        return float(vario[0, 0, 0]), float(vario[0, 0, 1]), float(vario[0, 0, 2])
+
+    def get_krig_params_batch(self, lat, lon, nnghs=None, rm_idx=None):
+        '''Batch form (new): all 12 months for arrays of points -> vario [n, 12, 3], status [n].'''
+        ss = self.stn_slct
+        return ss.ctx.fit_vario(lat, lon, mth=0, nnghs=nnghs, rm_idx=rm_idx, rm_zero=ss.rm_zero_dist_stns)
+
+
+class KrigTairAll(object):
+    '''
+    Moving window variogram fitting and regression kriging of monthly normals all in one step (interp_tair.py:700-768,
+    R krig_all interp.R:147-159); used to optimise the local number of neighbouring stations (step 21).
+    '''
+
+    def __init__(self, stn_slct):
+        self.stn_slct = stn_slct
+
+    def krigall(self, pt, nnghs, stns_rm=None):
+        '''Returns the 12 interpolated monthly normals at `pt` using `nnghs` neighbours.'''
+        ss = self.stn_slct
+        ctx = ss.ctx
+        mean, var, vario, st = ctx.krig_all(pt[LAT], pt[LON], pt[ELEV], _pt_lst(pt), int(nnghs),
+                                            rm_idx=ctx.rm_indices(stns_rm), rm_zero=ss.rm_zero_dist_stns)
+        _raise_status(st[0])
+        return mean[0]
 
 
 class InterpTair(object):

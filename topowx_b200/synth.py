@@ -57,6 +57,17 @@ class Fields(object):
         a = amp ** amp_pow
         return np.sum(a * np.sin(kx * lon + ky * lat + ph), axis=-1) / np.sqrt(np.sum(a * a) / 2.0)
 
+    @staticmethod
+    def _sum_grid(w, lon1d, lat1d, amp_pow=1.0):
+        """_sum on the grid lat1d x lon1d through the angle-addition identity: two (ny x waves)(waves x nx) products
+        instead of an [ny, nx, waves] temporary (same field to ~1e-15; used for whole-raster generation)."""
+        kx, ky, ph, amp = w
+        a = (amp ** amp_pow)
+        ax = kx[:, None] * np.asarray(lon1d, dtype=np.float64)[None, :] + ph[:, None]      # [waves, nx]
+        by = np.asarray(lat1d, dtype=np.float64)[:, None] * ky[None, :]                    # [ny, waves]
+        g = (np.cos(by) * a[None, :]) @ np.sin(ax) + (np.sin(by) * a[None, :]) @ np.cos(ax)
+        return g / np.sqrt(np.sum(a * a) / 2.0)
+
     def elev(self, lon, lat):
         z = self._sum(self.w_elev, lon, lat)                      # ~N(0,1)
         west = 1.0 / (1.0 + np.exp((np.asarray(lon) + 100.0) / 3.0))   # mountains in the west
@@ -213,6 +224,48 @@ def make_wrk_chk(fields, row0, col0, ny, nx):
     for m in range(1, 13):
         w[8 + m - 1] = fields.lst(0, m, lon2, lat2, elev)
         w[20 + m - 1] = fields.lst(1, m, lon2, lat2, elev)
+    return w
+
+
+def make_wrk_chk_grid_mask(fields, row0, col0, ny, nx):
+    """Plane 2 (land mask) of make_wrk_chk_grid alone, as a boolean array (whole-grid masks for Tiler)."""
+    lat = grid_lats(np.arange(row0, row0 + ny))
+    lon = grid_lons(np.arange(col0, col0 + nx))
+    lon2, lat2 = np.meshgrid(lon, lat)
+    inside = ((lat2 < GRID_LAT_TOP) & (lat2 > GRID_LAT_TOP - GRID_NROWS * RES)
+              & (lon2 > GRID_LON_LEFT) & (lon2 < GRID_LON_LEFT + GRID_NCOLS * RES))
+    x = (lon2 - (GRID_LON_LEFT + 29.17)) / 29.17
+    y = (lat2 - (GRID_LAT_TOP - 13.54)) / 13.54
+    return inside & ((1.0 - (np.abs(x) ** 3 + np.abs(y) ** 3)) + 0.12 * Fields._sum_grid(fields.w_coast, lon, lat) > 0.5)
+
+
+def make_wrk_chk_grid(fields, row0, col0, ny, nx):
+    """make_wrk_chk for large windows: the same analytic fields evaluated through Fields._sum_grid (agrees with
+    make_wrk_chk to ~1e-12 in every plane; the land mask and the climate divisions are identical away from exact ties)."""
+    lat = grid_lats(np.arange(row0, row0 + ny))
+    lon = grid_lons(np.arange(col0, col0 + nx))
+    lon2, lat2 = np.meshgrid(lon, lat)
+    f = fields
+    sg = lambda w: Fields._sum_grid(w, lon, lat)
+    w = np.empty((32, ny, nx), dtype=np.float64)
+    rc = np.mgrid[0:ny, 0:nx]
+    w[0], w[1] = rc[0], rc[1]
+    inside = ((lat2 < GRID_LAT_TOP) & (lat2 > GRID_LAT_TOP - GRID_NROWS * RES)
+              & (lon2 > GRID_LON_LEFT) & (lon2 < GRID_LON_LEFT + GRID_NCOLS * RES))
+    x = (lon2 - (GRID_LON_LEFT + 29.17)) / 29.17
+    y = (lat2 - (GRID_LAT_TOP - 13.54)) / 13.54
+    w[2] = inside & ((1.0 - (np.abs(x) ** 3 + np.abs(y) ** 3)) + 0.12 * sg(f.w_coast) > 0.5)
+    w[3], w[4] = lat2, lon2
+    west = 1.0 / (1.0 + np.exp((lon2 + 100.0) / 3.0))
+    elev = np.clip(300.0 + 1700.0 * west + (250.0 + 900.0 * west) * sg(f.w_elev), 0.0, 4000.0)
+    w[5] = elev
+    w[6] = np.clip(0.5 + 0.22 * sg(f.w_tdi), 0.0, 1.0)
+    w[7] = f.climdiv(lon2, lat2)
+    lst_w = [1.5 * sg(f.w_lst[0]), 1.5 * sg(f.w_lst[1])]
+    common = -0.0055 * elev - 0.75 * (lat2 - 38.0)
+    for m in range(1, 13):
+        w[8 + m - 1] = (6.0 + 11.0 * f._season(m)) + common + lst_w[0]
+        w[20 + m - 1] = (22.0 + 14.0 * f._season(m)) + common + lst_w[1]
     return w
 
 

@@ -7,7 +7,7 @@ scripts/step23 (XvalTairAnom.run_xval for every in-domain, non-bad station over 
     torchrun --nproc-per-node N scripts/step23_xval_anom_nnghs.py tmax ...
 
 The reference sends one station id per MPI message; here the stations are split contiguously over the ranks and each
-rank runs XvalTairAnom.run_xval_batch (one twxi_gwr_mth call per (neighbour count, month) over its batch of stations).
+rank runs XvalTairAnom.run_xval_batch (one twxi_xval_anom call per batch of stations: the neighbour search runs once, counts and months loop on the device).
 Writing the optimal counts back into the station database (set_optim_nstns_tair_anom) stays on the reference path.
 '''
 import argparse

@@ -188,3 +188,49 @@ def test_tile_writer_roundtrip(tmp_path):
         assert nbytes > tile["tmin"].nbytes * 2
     raw = np.load(os.path.join(str(tmp_path / "raw"), tid, "%s_tmax.npy" % tid))
     assert np.array_equal(raw, tile["tmax"])
+
+
+def test_predictor_store_and_tile_feed(tmp_path):
+    """rasters on disk -> Tiler -> TileFeed (background reader, ring of buffers): every tile arrives once,
+    in the reference's order, with the planes Tiler.next would build."""
+    from topowx_b200 import synth
+    from topowx_b200.interp import Tiler, PredictorStore, TileFeed
+    f = synth.Fields()
+    store = PredictorStore.create_synthetic(str(tmp_path / "rasters"), f, 240, 1230, 40, 60, band=16)
+    tiler = Tiler(store, store.attrs(), 20, 20, 20, 20)
+    assert tiler.chk_size_i == 32
+    ref = synth.make_wrk_chk_grid(f, 240, 1230, 40, 60)
+    seen = []
+    feed = TileFeed(tiler, depth=3, pinned=False)
+    for k, tid, wrk in feed:
+        _, i, j, y, x = tiler.tile_chks[len(seen)]
+        assert tid == tiler.tile_ids[k]
+        w = wrk.numpy()
+        np.testing.assert_array_equal(w[2], ref[2, i:i + 20, j:j + 20])
+        np.testing.assert_allclose(w[3:], ref[3:, i:i + 20, j:j + 20], rtol=0, atol=1e-9)
+        assert w[0, 3, 5] == 3 and w[1, 3, 5] == 5
+        seen.append(k)
+    assert seen == [c[0] for c in tiler.tile_chks] and len(seen) == tiler.ntiles
+    assert feed.bytes_read == len(seen) * 32 * 400 * 8
+
+
+def test_station_data_wrk_chk_cache():
+    """StationDataWrkChk.set_obs / load_obs (interp_tair.py:1027-1097): DB-order columns, buffer grows until all found."""
+    from topowx_b200 import synth
+    from topowx_b200.interp import StationDataWrkChk
+    f = synth.Fields()
+    days = synth.make_days(1995, 1)
+    da = synth.make_station_db(0, 300, synth.tile_bbox(buf=4.0), f, days)
+    wc = StationDataWrkChk((da.stns, da.var, da.days), "tmin")
+    b = synth.tile_bbox(buf=0.0)
+    wc.set_obs(b, deg_buf=1)
+    n1 = wc.chk_stnids.size
+    assert 0 < n1 < 300
+    inside = wc.chk_stnids[[5, 1, 9]]
+    got = wc.load_obs(inside, mth=3)
+    want = da.load_obs(np.sort(inside), mth=3)
+    np.testing.assert_array_equal(got, want)                      # DB (= id) order, whatever the request order
+    far = np.setdiff1d(da.stn_ids, wc.chk_stnids)[:2]
+    got = wc.load_obs(np.concatenate([inside, far]), mth=7)
+    assert wc.chk_deg_buf > 1 and got.shape == (31, 5)
+    np.testing.assert_array_equal(got, da.load_obs(np.sort(np.concatenate([inside, far])), mth=7))

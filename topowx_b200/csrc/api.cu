@@ -264,6 +264,28 @@ int twxi_ctx_create(twxi_ctx** out, int device, int n, const double* lon, const 
     up(&st.lst, lst, n12); up(&st.norm, norm, n12); up(&st.optim, optim_nnghs, n12);
     up(&st.optim_anom, optim_nnghs_anom, n12); up(&st.nug, vario_nug, n12); up(&st.psill, vario_psill, n12);
     up(&st.rng, vario_rng, n12);
+    {   // station-major copies for the neighbour-count / variogram smoothing (setup.cu)
+        std::vector<double> o2((size_t)n * 24), v2((size_t)n * 36);
+        for (int m = 0; m < 12; ++m)
+            for (int i = 0; i < n; ++i) {
+                o2[(size_t)i * 24 + m] = optim_nnghs[(size_t)m * n + i];
+                o2[(size_t)i * 24 + 12 + m] = optim_nnghs_anom[(size_t)m * n + i];
+                v2[(size_t)i * 36 + m * 3] = vario_nug[(size_t)m * n + i];
+                v2[(size_t)i * 36 + m * 3 + 1] = vario_psill[(size_t)m * n + i];
+                v2[(size_t)i * 36 + m * 3 + 2] = vario_rng[(size_t)m * n + i];
+            }
+        std::vector<double> gx((size_t)12 * n * 8);
+        for (int m = 0; m < 12; ++m)
+            for (int i = 0; i < n; ++i) {
+                double* g = gx.data() + ((size_t)m * n + i) * 8;
+                g[0] = 1.0; g[1] = lon[i]; g[2] = lat[i]; g[3] = elev[i]; g[4] = tdi[i];
+                g[5] = lst[(size_t)m * n + i]; g[6] = norm[(size_t)m * n + i]; g[7] = 0.0;
+            }
+        up(&st.gx, gx.data(), gx.size());
+        up(&st.optim2, o2.data(), o2.size());
+        up(&st.vario2, v2.data(), v2.size());
+        if (rc == TWXI_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) { set_error("upload failed"); rc = TWXI_ERR_CUDA; }
+    }
     double *lonrad = nullptr, *latrad = nullptr, *coslat = nullptr, *H = nullptr;
     if (rc == TWXI_OK) rc = dev_alloc(c->owned, &lonrad, n);
     if (rc == TWXI_OK) rc = dev_alloc(c->owned, &latrad, n);

@@ -331,17 +331,18 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
         }
         // ---- augmented rows -B' = -[1, dlon, dlat, delev, dlst, y - yref, c0]' into tile row NB: one station per
         // thread, all its gathers in flight at once (the indices were prefetched during the previous problem)
-        const double* lstm = a.st.lst + (size_t)m * N;
         const double* normm = a.st.norm + (size_t)m * N;
+        const double* gxm = a.st.gx + (size_t)m * N * 8;      // station rows (1, lon, lat, elev, tdi, lst_m, norm_m, 0)
         const double yref = normm[s_first];
         double gl[NJ][6];
 #pragma unroll
         for (int t = 0; t < NJ; ++t) {
             const int j = tid + t * NT;
             if (j < n) {
-                const int s = sj[t];
-                gl[t][0] = a.st.lon[s]; gl[t][1] = a.st.lat[s]; gl[t][2] = a.st.elev[s];
-                gl[t][3] = lstm[s]; gl[t][4] = normm[s]; gl[t][5] = a.h0[(size_t)q * a.k1 + j];
+                const double2* g2 = reinterpret_cast<const double2*>(gxm + (size_t)sj[t] * 8);    // one 64-byte row
+                const double2 ga = g2[0], gb = g2[1], gc = g2[2], gd = g2[3];
+                gl[t][0] = ga.y; gl[t][1] = gb.x; gl[t][2] = gb.y;
+                gl[t][3] = gc.y; gl[t][4] = gd.x; gl[t][5] = a.h0[(size_t)q * a.k1 + j];
             }
         }
         const double* vp = a.vario_is_override ? a.vario + (size_t)q * 3 : a.vario + ((size_t)q * 12 + m) * 3;

@@ -55,33 +55,32 @@ __global__ void __launch_bounds__(SETUP_THREADS) nngh_params_kernel(SetupArgs a)
     } else if (k1 <= ninit) {
         st = TWXI_ST_TOO_FEW_STNS;                             // IndexError: set_ngh_stns(100) with < 101 stations
     } else {
+        // lane L < 24 owns one (kind, month) column of the station-major table: L = month for optim_nnghs, 12 + month for
+        // optim_nnghs_anom.  Per neighbour the warp reads ONE 192-byte run; weights and indices are staged per warp.
+        __shared__ double s_w[SETUP_THREADS / 32][TWXI_INIT_NNGHS];
+        __shared__ int s_s[SETUP_THREADS / 32][TWXI_INIT_NNGHS];
+        const int wq = threadIdx.x >> 5;
         const double dbw = dist[ninit];
-        double w[4];
-        int si[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            int j = lane + 32 * t;
-            bool ok = j < ninit;
-            w[t] = ok ? bisquare(dist[j], dbw) : 0.0;
-            si[t] = ok ? idx[j] : 0;
+        for (int j = lane; j < ninit; j += 32) {
+            s_w[wq][j] = bisquare(dist[j], dbw);
+            s_s[wq][j] = idx[j];
         }
-        for (int m = 0; m < 12; ++m) {
-            double num = 0, den = 0, num2 = 0, den2 = 0;
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                if (lane + 32 * t < ninit) {
-                    double v = a.st.optim[(size_t)m * n + si[t]];
-                    if (isfinite(v)) { num += v * w[t]; den += w[t]; }
-                    double v2 = a.st.optim_anom[(size_t)m * n + si[t]];
-                    if (isfinite(v2)) { num2 += v2 * w[t]; den2 += w[t]; }
-                }
+        __syncwarp();
+        double num = 0.0, den = 0.0;
+        if (lane < 24) {
+            const double* col = a.st.optim2 + lane;
+#pragma unroll 4
+            for (int j = 0; j < ninit; ++j) {
+                const double v = col[(size_t)s_s[wq][j] * 24];
+                const double w = s_w[wq][j];
+                if (isfinite(v)) { num += v * w; den += w; }
             }
-            // finite-count is implied by den > 0 unless every finite neighbour has weight 0 (ZeroDivisionError
-            // in np.average -> same per-point failure)
-            num = warp_sum(num); den = warp_sum(den); num2 = warp_sum(num2); den2 = warp_sum(den2);
-            int kn = -1, ka = -1;
-            if (den > 0) kn = (int)rint(num / den);              // np.round: half to even
-            if (den2 > 0) ka = (int)rint(num2 / den2);
+        }
+        // finite-count is implied by den > 0 unless every finite neighbour has weight 0 (ZeroDivisionError in np.average ->
+        // same per-point failure); np.round: half to even
+        const int kmine = den > 0 ? (int)rint(num / den) : -1;
+        for (int m = 0; m < 12; ++m) {
+            int kn = __shfl_sync(0xffffffffu, kmine, m), ka = __shfl_sync(0xffffffffu, kmine, 12 + m);
             if (a.norm_override) kn = a.norm_override[q];
             if (a.anom_override) ka = a.anom_override[q];
             const bool need_m = a.only_mth == 0 || a.only_mth == m + 1;
@@ -108,14 +107,14 @@ __global__ void __launch_bounds__(SETUP_THREADS) nngh_params_kernel(SetupArgs a)
             const double dbw = dist[k];
             double sw = 0, snug = 0, sps = 0, srg = 0;
             for (int j = lane; j < k; j += 32) {
-                int s = idx[j];
-                double vn = a.st.nug[(size_t)m * n + s];
+                const double* v = a.st.vario2 + (size_t)idx[j] * 36 + m * 3;    // (nug, psill, rng): one 24-byte run
+                const double vn = v[0];
                 if (isfinite(vn)) {
                     double w = bisquare(dist[j], dbw);
                     sw += w;
                     snug += vn * w;
-                    sps += a.st.psill[(size_t)m * n + s] * w;
-                    srg += a.st.rng[(size_t)m * n + s] * w;
+                    sps += v[1] * w;
+                    srg += v[2] * w;
                 }
             }
             sw = warp_sum(sw); snug = warp_sum(snug); sps = warp_sum(sps); srg = warp_sum(srg);

@@ -55,6 +55,12 @@ struct StnTable {
     const double* nug;
     const double* psill;
     const double* rng;
+    const double* gx;       // [12][n][8] station-major predictor rows per month: (1, lon, lat, elev, tdi, lst_m, norm_m, 0):
+                            //         one 64-byte run per neighbour for the GWR normal equations / hat row and for the
+                            //         augmented rows of the kriging system, instead of 5-6 scattered sectors
+    const double* optim2;   // [n][24] station-major copy: optim_nnghs 01-12, optim_nnghs_anom 01-12 (one 192-byte run per
+                            //         station instead of 24 sectors: the smoothing of a4 reads the 100 nearest stations)
+    const double* vario2;   // [n][12][3] station-major copy: (nug, psill, rng) per month
     const double* H;        // [n][n] WGS-84 great-circle distance (km) between stations, rows/columns in hpos order
     const int32_t* hpos;    // [n] row/column of a station in H (Morton order of lon/lat: a point's neighbours
                             //     share 32-byte sectors of H, so the tile gather of the kriging stage reads ~3x less from L2)

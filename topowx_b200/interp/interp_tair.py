@@ -259,9 +259,11 @@ class PtInterpTair(object):
 
 class StationDataWrkChk(StationSerialDataDb):
     '''
-    StationSerialDataDb wrapper that preloads the observations of a lon/lat box (interp_tair.py:997-1097).
-    On the GPU path the whole observation table is resident in HBM, so set_obs only records the box; load_obs
-    keeps the reference's contract (columns in DB order) for callers that want host arrays.
+    StationSerialDataDb wrapper that preloads and caches all station observations within a lon/lat bounding box
+    (interp_tair.py:997-1097), with the reference's contract: `set_obs` caches the columns of the stations inside the box
+    +/- deg_buf split by month, `load_obs(ids, mth)` returns them in DB order and grows the buffer by one degree until
+    every requested station is found.  The GPU path does not need it (the whole observation table is resident in HBM,
+    twxi_ctx_set_obs); it serves host-side callers written against the reference.
     '''
 
     def __init__(self, nc_path, var_name, vcc_size=None, vcc_nelems=None, vcc_preemption=None):
@@ -276,9 +278,23 @@ class StationDataWrkChk(StationSerialDataDb):
         minLon, maxLon = bnds[2] - deg_buf, bnds[3] + deg_buf
         maskStns = np.logical_and(np.logical_and(self.stns[LAT] >= minLat, self.stns[LAT] <= maxLat),
                                   np.logical_and(self.stns[LON] >= minLon, self.stns[LON] <= maxLon))
-        self.chk_stnids = np.take(self.stn_ids, np.nonzero(maskStns)[0])
+        maskStns = np.nonzero(maskStns)[0]
+        self.chk_stnids = np.take(self.stn_ids, maskStns)
+        achkObs = self.var[:, maskStns]
+        self.chk_obs = {mth: np.take(achkObs, self.mth_idx[mth], axis=0) for mth in range(1, 13)}
         self.chk_deg_buf = deg_buf
         self.chk_bnds = bnds
 
     def load_obs(self, stn_ids, mth=None):
-        return StationSerialDataDb.load_obs(self, stn_ids, mth)
+        if mth is None:
+            return StationSerialDataDb.load_obs(self, stn_ids, mth)
+        if self.chk_obs is None:
+            raise Exception("set_obs has not been called")
+        stn_ids = np.atleast_1d(stn_ids)
+        mask = np.nonzero(np.isin(self.chk_stnids, stn_ids))[0]
+        while mask.size != stn_ids.size:                          # :1089-1093 "Increasing obs chunk..."
+            if self.chk_stnids.size == self.stn_ids.size:
+                raise KeyError("station id not in the database")
+            self.set_obs(self.chk_bnds, self.chk_deg_buf + 1)
+            mask = np.nonzero(np.isin(self.chk_stnids, stn_ids))[0]
+        return np.take(self.chk_obs[mth], mask, axis=1)

@@ -46,6 +46,7 @@ struct GwrArgs {
     int xv_nc, xv_ci;
 };
 
+template <bool XVAL>
 __global__ void __launch_bounds__(GWR_THREADS, 4) gwr_kernel(GwrArgs a) {
     __shared__ __align__(16) double s_z[GWR_WARPS][GWR_MAXK];
     __shared__ __align__(16) int s_off[GWR_WARPS][GWR_MAXK];                // station * ndays: row offset into obsT
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(GWR_THREADS, 4) gwr_kernel(GwrArgs a) {
     const int q = (int)(item % a.npts);
     const int m = a.single_mth >= 0 ? a.single_mth : (int)(item / a.npts);
     if (a.status[q] != TWXI_ST_OK) return;
-    const int k = a.k_fixed > 0 ? a.k_fixed : a.nn[(size_t)q * 24 + 12 + m];
+    const int k = XVAL ? a.k_fixed : a.nn[(size_t)q * 24 + 12 + m];
     if (k < 1) return;
     const int N = a.st.n;
     const int32_t* idx = a.idx + (size_t)q * a.k1;
@@ -150,11 +151,11 @@ __global__ void __launch_bounds__(GWR_THREADS, 4) gwr_kernel(GwrArgs a) {
     zn = warp_sum(zn);
     if (a.hat_k && lane == 0) a.hat_k[q] = k;
     __syncwarp();
-    if (!a.daily && !a.out_month && !a.xv_out) return;
+    if (!XVAL && !a.daily && !a.out_month) return;
 
     // ---- daily values: lanes = days of the month, neighbours gathered from the station-major obs table ------------
-    const int self = a.xv_self ? a.xv_self[q] : 0;
-    const double ptn = a.xv_self ? normm[self] : (a.pt_norm_single ? a.pt_norm[q] : a.pt_norm[(size_t)q * 12 + m]);
+    const int self = XVAL ? a.xv_self[q] : 0;
+    const double ptn = XVAL ? normm[self] : (a.pt_norm_single ? a.pt_norm[q] : a.pt_norm[(size_t)q * 12 + m]);
     const double off = ptn - zn;
     const int p0 = a.ob.moff[m], D = a.ob.moff[m + 1] - p0;
     double sd = 0.0, sad = 0.0, sx = 0.0, sy = 0.0, sxx = 0.0, syy = 0.0, sxy = 0.0;    // xval sums over the days of this lane
@@ -177,9 +178,9 @@ __global__ void __launch_bounds__(GWR_THREADS, 4) gwr_kernel(GwrArgs a) {
         for (; j < k; ++j) acc0 = fma(s_z[warp][j], (double)col[s_off[warp][j]], acc0);
         const double v = ((acc0 + acc1) + (acc2 + acc3)) + off;
         if (valid) {
-            if (a.daily) a.daily[(size_t)q * nd + a.ob.day_of_pos[p0 + d]] = v;
-            if (a.out_month) a.out_month[(size_t)q * D + d] = v;
-            if (a.xv_out) {                                   // optimize.py:520-531
+            if (!XVAL && a.daily) a.daily[(size_t)q * nd + a.ob.day_of_pos[p0 + d]] = v;
+            if (!XVAL && a.out_month) a.out_month[(size_t)q * D + d] = v;
+            if (XVAL) {                                       // optimize.py:520-531
                 const double x = v - ptn;                                        // interpolated anomaly
                 const double y = (double)a.ob.obsT[(size_t)self * nd + p0 + d] - ptn;    // the station's own anomaly
                 const double dif = x - y;
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(GWR_THREADS, 4) gwr_kernel(GwrArgs a) {
             }
         }
     }
-    if (a.xv_out) {
+    if (XVAL) {
         sd = warp_sum(sd); sad = warp_sum(sad); sx = warp_sum(sx); sy = warp_sum(sy);
         sxx = warp_sum(sxx); syy = warp_sum(syy); sxy = warp_sum(sxy);
         if (lane == 0) {
@@ -212,7 +213,7 @@ int launch_gwr_xval(Ctx& c, Batch& b, const int32_t* self, const int32_t* counts
     const long long items = (long long)b.npts * 12;
     for (int i = 0; i < ncounts; ++i) {
         a.k_fixed = counts_host[i]; a.xv_ci = i;
-        gwr_kernel<<<(unsigned)((items + GWR_WARPS - 1) / GWR_WARPS), GWR_THREADS, 0, c.stream>>>(a);
+        gwr_kernel<true><<<(unsigned)((items + GWR_WARPS - 1) / GWR_WARPS), GWR_THREADS, 0, c.stream>>>(a);
         TWXI_LAUNCH_CHECK();
     }
     return TWXI_OK;
@@ -242,7 +243,7 @@ int launch_gwr(Ctx& c, Batch& b, int mth, const double* pt_norm_override, int wr
     a.kmax = kmax; a.hat_k = hat_k; a.hat_idx = hat_idx; a.hat_z = hat_z;
     a.status = b.status;
     const long long items = (long long)b.npts * (mth >= 1 ? 1 : 12);
-    gwr_kernel<<<(unsigned)((items + GWR_WARPS - 1) / GWR_WARPS), GWR_THREADS, 0, c.stream>>>(a);
+    gwr_kernel<false><<<(unsigned)((items + GWR_WARPS - 1) / GWR_WARPS), GWR_THREADS, 0, c.stream>>>(a);
     TWXI_LAUNCH_CHECK();
     return TWXI_OK;
 }

@@ -49,7 +49,8 @@ constexpr int KED_HDR = 8 + 64 + 2 * 128;         // doubles: flag + mbarrier, 2
 // ---- 1. compact distance tiles -------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) hgather_kernel(StnTable st, int q0, int nq, int k1, const int32_t* idx,
                                                       const int32_t* nn, int32_t* status, double* hc,
-                                                      size_t hc_stride, int single_mth, int nbcap) {
+                                                      size_t hc_stride, int single_mth, int nbcap, const double* vario,
+                                                      int vario_is_override, int off_cp) {
     __shared__ int sidx[256];
     const int q = q0 + blockIdx.x;
     if (status[q] != TWXI_ST_OK) return;
@@ -66,6 +67,14 @@ __global__ void __launch_bounds__(256) hgather_kernel(StnTable st, int q0, int n
     const int NB = (nmax + 7) >> 3;
     const int N = st.n;
     double* out = hc + (size_t)blockIdx.x * hc_stride;
+    if (threadIdx.x < 12) {                                   // covariance parameters of the 12 monthly systems, once per point
+        const int m = threadIdx.x;                            // (every thread of every solving CTA used to derive them itself)
+        const double* vp = vario_is_override ? vario + (size_t)q * 3 : vario + ((size_t)q * 12 + m) * 3;
+        CovPar cp;
+        covpar_set(cp, vp[0], vp[1], vp[2]);
+        double* c = out + off_cp + m * 8;
+        c[0] = cp.c00; c[1] = cp.nir; c[2] = cp.nk; c[3] = cp.c0; c[4] = cp.c2; c[5] = cp.c3; c[6] = cp.c4; c[7] = cp.c5;
+    }
     for (int I = 0; I < NB; ++I) {
         const int cnt = (I + 1) * 64;
         double* row = out + (size_t)htile(I, 0) * 64;
@@ -345,8 +354,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
                 gl[t][3] = gc.y; gl[t][4] = gd.x; gl[t][5] = a.h0[(size_t)q * a.k1 + j];
             }
         }
-        const double* vp = a.vario_is_override ? a.vario + (size_t)q * 3 : a.vario + ((size_t)q * 12 + m) * 3;
-        const double nug = vp[0], psill = vp[1], rng = vp[2];
+        const double2* cpg = reinterpret_cast<const double2*>(hc + a.off_cp + m * 8);    // staged by hgather_kernel
+        const double2 cp0 = cpg[0], cp1 = cpg[1], cp2 = cpg[2], cp3 = cpg[3];
         const double lon0 = a.qlon[q], lat0 = a.qlat[q], elev0 = a.qelev[q], lst0 = a.qlst[(size_t)q * 12 + m];
         // raw distances of the diagonal tiles 0, 1 (-> N_diag buffers) and 2 (first look-ahead column)
         double2 hd = make_double2(0.0, 0.0), hd1 = make_double2(0.0, 0.0);
@@ -355,7 +364,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
             if (NB > 1) hd1 = p.hc2[htile(1, 1) * 32];
         }
         if (warp == NW - 1 && NB > 2) hd = p.hc2[htile(2, 2) * 32];     // look-ahead worker (u == 0)
-        covpar_set(p.cp, nug, psill, rng);
+        p.cp.c00 = cp0.x; p.cp.nir = cp0.y; p.cp.nk = cp1.x; p.cp.c0 = cp1.y;
+        p.cp.c2 = cp2.x; p.cp.c3 = cp2.y; p.cp.c4 = cp3.x; p.cp.c5 = cp3.y;
         if (warp == NW && pending) {
             ked_finish(a.mean, a.var, a.status, pend_S, pend_q, pend_m, pend_yref, pend_c00, lane);
             pending = false;
@@ -601,7 +611,8 @@ int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
     // largest possible n is k1 - 1; points whose k_norm exceeds this build's limit (TWXI_MAX_KRIG_NNGHS) get TWXI_ST_LIMIT
     // (hgather_kernel) instead of failing the whole call
     const int nbmax = std::min((b.k1 - 1 + 7) / 8, KED_NBMAX);
-    const size_t hc_stride = (size_t)nbmax * (nbmax + 1) / 2 * 64;
+    const int off_cp = nbmax * (nbmax + 1) / 2 * 64;          // after the tiles: 12 x 8 covariance parameters
+    const size_t hc_stride = (size_t)off_cp + 12 * 8;
     // points per sub-batch so that the compact distance buffer stays within its budget
     size_t budget = (size_t)6 << 30;
     if (const char* e = getenv("TWXI_HC_BUDGET_MB")) budget = (size_t)atoll(e) << 20;
@@ -629,8 +640,7 @@ int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
     KedArgs a;
     a.st = c.st; a.npts = b.npts; a.k1 = b.k1;
     a.idx = b.idx; a.h0 = b.h0; a.nn = b.nn;
-    a.vario = vario_override ? vario_override : b.vario;
-    a.vario_is_override = vario_override != nullptr;
+    a.off_cp = off_cp;
     a.qlon = b.lon; a.qlat = b.lat; a.qelev = b.elev; a.qlst = b.lst;
     a.hc = w.hc; a.hc_stride = hc_stride; a.list = w.list; a.bstart = bstart; a.bcount = bcount;
     a.mean = b.mean; a.var = b.var; a.status = b.status;
@@ -639,7 +649,8 @@ int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
     for (int q0 = 0; q0 < b.npts; q0 += qcap) {
         const int nq = std::min(qcap, b.npts - q0);
         a.q0 = q0;
-        hgather_kernel<<<nq, 256, 0, c.stream>>>(c.st, q0, nq, b.k1, b.idx, b.nn, b.status, w.hc, hc_stride, mth >= 1 ? mth - 1 : -1, nbmax);
+        hgather_kernel<<<nq, 256, 0, c.stream>>>(c.st, q0, nq, b.k1, b.idx, b.nn, b.status, w.hc, hc_stride, mth >= 1 ? mth - 1 : -1, nbmax,
+                                                      vario_override ? vario_override : b.vario, vario_override != nullptr, off_cp);
         TWXI_LAUNCH_CHECK();
         const int nt = nq * 12, nblk = (nt + 255) / 256;
         ked_bin_kernel<<<nblk, 256, 0, c.stream>>>(q0, nq, single, b.nn, b.status, w.blockcnt);

@@ -19,8 +19,7 @@ struct KedArgs {
     const int32_t* idx;
     const double* h0;
     const int32_t* nn;
-    const double* vario;       // [npts][12][3], or [npts][3] when vario_is_override
-    int vario_is_override;
+    int off_cp;                // offset (doubles) of the 12 x 8 covariance parameters inside a point's staged block
     const double* qlon;
     const double* qlat;
     const double* qelev;

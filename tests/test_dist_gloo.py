@@ -58,3 +58,63 @@ def test_two_rank_partition_is_consistent():
     assert sorted(union) == sorted(chks) and len(union) == len(set(union))
     assert tmax == 2.0
     assert total_cells == nmask - 0          # every unmasked cell of a processed tile is counted exactly once
+
+
+def _pull_worker(rank, world, port, q):
+    """bench.py's strong-scaling scheduler: ranks pull tile indices from a shared counter (the coordinator rank of
+    step25:293-305); two passes with separate keys, all_gather of the per-rank statistics as in bench.py."""
+    import sys
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    import time
+    puller = bench.Puller(world)
+    NT = 23
+    got = []
+    for key in ("p0", "p1"):
+        mine = []
+        while True:
+            i = puller.next(key)
+            if i >= NT:
+                break
+            mine.append(i)
+            time.sleep(0.002 * (1 + rank))            # unequal speeds: the faster rank pulls more
+        got.append(mine)
+    stats = torch.tensor([float(len(got[0]) + len(got[1])), 10.0 + rank], dtype=torch.float64)
+    allst = [torch.zeros_like(stats) for _ in range(world)]
+    dist.all_gather(allst, stats)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, got)
+    if rank == 0:
+        q.put((gathered, torch.stack(allst).numpy().tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_dynamic_pull_covers_every_tile_once():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pull_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    gathered, allst = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for k in range(2):
+        union = sorted(gathered[0][k] + gathered[1][k])
+        assert union == list(range(23))                # every tile exactly once per pass
+    assert len(gathered[0][0]) > len(gathered[1][0])   # the faster rank took more: dynamic, not static
+    assert sum(r[0] for r in allst) == 46 and max(r[1] for r in allst) == 11.0
+
+
+def test_single_rank_puller_is_a_local_counter():
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    p = bench.Puller(1)
+    assert [p.next("a") for _ in range(3)] == [0, 1, 2] and p.next("b") == 0

@@ -114,6 +114,33 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(KnnArgs a) {
     if (tid == 0) { s_prefix = 0ull; s_remaining = (unsigned)k1; s_cnt = 0u; }
     __syncthreads();
 
+    // ---- fast path (pruned candidate lists): at most one candidate per thread.  Every key is ranked directly by counting
+    // the strictly smaller keys (one 64-bit compare per pair, broadcast reads); no select passes, no compaction, two
+    // barriers.  Equal keys get equal ranks: a collision among the first k1 ranks (an exact distance tie, decided by the
+    // station index) sends the query to the general path below, which sorts on (key, index).
+    bool fast_done = false;
+    if (n <= KNN_THREADS) {
+        const unsigned long long mk = tid < n ? keys[tid] : ~0ull;
+        const int valid = __syncthreads_count(mk != ~0ull);
+        if (valid < k1) {                                      // IndexError at station_select.py:164
+            if (tid == 0) a.status[q] = TWXI_ST_TOO_FEW_STNS;
+            return;
+        }
+        int rank = 0;
+        int j = 0;
+        for (; j + 3 < n; j += 4) {
+            const unsigned long long k0 = keys[j], k1v = keys[j + 1], k2 = keys[j + 2], k3 = keys[j + 3];
+            rank += (k0 < mk) + (k1v < mk) + (k2 < mk) + (k3 < mk);
+        }
+        for (; j < n; ++j) rank += keys[j] < mk;
+        const int mi = cand ? (tid < n ? cand[tid] : 0) : tid;
+        const bool mine = mk != ~0ull && rank < k1;
+        if (mine) { selkey[rank] = mk; selidx[rank] = mi; }
+        __syncthreads();
+        const int collide = __syncthreads_or(mine && selidx[rank] != mi);
+        fast_done = !collide;
+    }
+    if (!fast_done) {
     // ---- phase 2: radix select of the k1-th smallest key -----------------------------------------
     for (int pass = 0; pass < 8; ++pass) {
         const int shift = 56 - 8 * pass;
@@ -195,6 +222,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(KnnArgs a) {
     } else {
         bitonic_sort(selkey, selidx, P);
     }
+    }   // general path
 
     // ---- phase 4: kilometres for the k1 survivors; verify (km, index) order ---------------------------
     int bad = 0;

@@ -19,6 +19,9 @@ namespace twxi {
 constexpr int GWR_THREADS = 256;
 constexpr int GWR_WARPS = GWR_THREADS / 32;
 constexpr int GWR_MAXK = 256;
+#ifndef TWXI_GWR_MINB
+#define TWXI_GWR_MINB 4
+#endif
 
 struct GwrArgs {
     StnTable st;
@@ -47,7 +50,7 @@ struct GwrArgs {
 };
 
 template <bool XVAL>
-__global__ void __launch_bounds__(GWR_THREADS, 4) gwr_kernel(GwrArgs a) {
+__global__ void __launch_bounds__(GWR_THREADS, TWXI_GWR_MINB) gwr_kernel(GwrArgs a) {
     __shared__ __align__(16) double s_z[GWR_WARPS][GWR_MAXK];
     __shared__ __align__(16) int s_off[GWR_WARPS][GWR_MAXK];                // station * ndays: row offset into obsT
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -532,6 +532,20 @@ def secondary_runs(ctx, da, tiles, wrk_h, wrk_d, out_d, out_h, stream, lib, args
         nst += int((st == 0).sum())
     dt = time.perf_counter() - t0
     sec["C3_loo_normals"] = {"stations_ok": nst, "wall_s_incl_copies": dt, "station_month_vars_per_s": nst * 12 / dt}
+    # ... and with the daily series (what step24 writes per station: daily f8[ndays] + norms[12], step24:67), in batches
+    t0 = time.perf_counter()
+    nst = 0
+    for c in ctx:
+        s = c.stns
+        lst = np.stack([s[db.get_lst_varname(m)] for m in range(1, 13)], axis=1)
+        for i0 in range(0, c.n, 4096):
+            sl = slice(i0, min(i0 + 4096, c.n))
+            rm = np.arange(sl.start, sl.stop, dtype=np.int32).reshape(-1, 1)
+            dly, norms, se, var, st = c.interp_points(s[db.LAT][sl], s[db.LON][sl], s[db.ELEV][sl], s[db.TDI][sl], lst[sl],
+                                                      rm_idx=rm, rm_zero=True, daily=True)
+            nst += int((st == 0).sum())
+    dt = time.perf_counter() - t0
+    sec["C3_loo_daily"] = {"stations_ok": nst, "wall_s_incl_copies": dt, "station_days_per_s": nst * NDAYS / dt}
     # bytes on disk: 8 tiles end to end with a background raw writer consuming every result (3 pinned sets in flight)
     tmp = tempfile.mkdtemp(prefix="twx_bench_")
     try:

@@ -168,6 +168,24 @@ __global__ void __launch_bounds__(GWR_THREADS, TWXI_GWR_MINB) gwr_kernel(GwrArgs
         const float* col = a.ob.obsT + p0 + (valid ? d : 0);
         double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
         int j = 0;
+        for (; j + 7 < k; j += 8) {                           // eight gathers in flight per pass (same order of the sums)
+            const int4 o4 = *reinterpret_cast<const int4*>(&s_off[warp][j]);
+            const int4 o8 = *reinterpret_cast<const int4*>(&s_off[warp][j + 4]);
+            const float f0 = col[o4.x], f1 = col[o4.y], f2 = col[o4.z], f3 = col[o4.w];
+            const float f4 = col[o8.x], f5 = col[o8.y], f6 = col[o8.z], f7 = col[o8.w];
+            const double2 za = *reinterpret_cast<const double2*>(&s_z[warp][j]);
+            const double2 zb = *reinterpret_cast<const double2*>(&s_z[warp][j + 2]);
+            const double2 zc = *reinterpret_cast<const double2*>(&s_z[warp][j + 4]);
+            const double2 zd = *reinterpret_cast<const double2*>(&s_z[warp][j + 6]);
+            acc0 = fma(za.x, (double)f0, acc0);
+            acc1 = fma(za.y, (double)f1, acc1);
+            acc2 = fma(zb.x, (double)f2, acc2);
+            acc3 = fma(zb.y, (double)f3, acc3);
+            acc0 = fma(zc.x, (double)f4, acc0);
+            acc1 = fma(zc.y, (double)f5, acc1);
+            acc2 = fma(zd.x, (double)f6, acc2);
+            acc3 = fma(zd.y, (double)f7, acc3);
+        }
         for (; j + 3 < k; j += 4) {                           // four gathers in flight per pass
             const int4 o4 = *reinterpret_cast<const int4*>(&s_off[warp][j]);
             const float f0 = col[o4.x], f1 = col[o4.y], f2 = col[o4.z], f3 = col[o4.w];

@@ -108,6 +108,7 @@ __device__ __forceinline__ double2 cov_tile(double2 h, int i, int j, int n, cons
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    __syncwarp();                                             // bar.sync is an aligned barrier: the warp must arrive converged
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

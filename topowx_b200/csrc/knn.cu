@@ -165,6 +165,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(KnnArgs a) {
             }
             unsigned excl = incl - sum;
             unsigned rem = s_remaining;
+            __syncwarp();                                      // every lane has read s_remaining before one lane updates it
             if (excl < rem && rem <= incl) {
                 unsigned r = rem - excl;
 #pragma unroll

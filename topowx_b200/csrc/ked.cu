@@ -201,10 +201,12 @@ __device__ __forceinline__ void stage_rows(const Prob& p, int K, int u, const do
         const double2* pA2 = tl2 + r2;
         const double2 n1 = pA1[K * 32], n2 = pA2[K * 32];
         double2 acc1 = pA1[K * 32 + 32], acc2 = pA2[K * 32 + 32];
-        double2 l1 = make_double2(0.0, 0.0), l2 = make_double2(0.0, 0.0);
-        dmma(l1, n1.x, negW.x); dmma(l2, n2.x, negW.x);
+        double2 l1, l2;
+        dmma_z(l1, n1.x, negW.x); dmma_z(l2, n2.x, negW.x);
         dmma(l1, n1.y, negW.y); dmma(l2, n2.y, negW.y);
-        double2 e1 = make_double2(0.0, 0.0), e2 = make_double2(0.0, 0.0);
+        double2 e1, e2;                                       // second accumulator pair: starts with the L(I,K) L(K+1,K)' term
+        dmma_z(e1, l1.x, lk1.x); dmma_z(e2, l2.x, lk1.x);
+        dmma(e1, l1.y, lk1.y); dmma(e2, l2.y, lk1.y);
         int J = 0;
         for (; J + 1 < K; J += 2) {
             const double2 b0 = pB[J * 32], b1 = pB[J * 32 + 32];
@@ -219,8 +221,6 @@ __device__ __forceinline__ void stage_rows(const Prob& p, int K, int u, const do
             dmma(acc1, a10.y, b0.y); dmma(acc2, a20.y, b0.y);
         }
         tl2[r1 + K * 32] = l1; tl2[r2 + K * 32] = l2;
-        dmma(e1, l1.x, lk1.x); dmma(e2, l2.x, lk1.x);
-        dmma(e1, l1.y, lk1.y); dmma(e2, l2.y, lk1.y);
         acc1.x += e1.x; acc1.y += e1.y; acc2.x += e2.x; acc2.y += e2.y;
         tl2[r1 + K * 32 + 32] = acc1; tl2[r2 + K * 32 + 32] = acc2;
         if (I == c) lfirst = l1;
@@ -231,9 +231,10 @@ __device__ __forceinline__ void stage_rows(const Prob& p, int K, int u, const do
         const double2 n1 = pA1[K * 32];
         double2 acc1 = make_double2(0.0, 0.0);
         if (I > K + 1) acc1 = pA1[K * 32 + 32];
-        double2 l1 = make_double2(0.0, 0.0);
-        dmma2(l1, n1, negW);
-        double2 e1 = make_double2(0.0, 0.0);
+        double2 l1;
+        dmma2_z(l1, n1, negW);
+        double2 e1;
+        dmma2_z(e1, l1, lk1);
         int J = 0;
         for (; J + 1 < K; J += 2) {
             const double2 b0 = pB[J * 32], a0 = pA1[J * 32], b1 = pB[J * 32 + 32], a1 = pA1[J * 32 + 32];
@@ -242,14 +243,14 @@ __device__ __forceinline__ void stage_rows(const Prob& p, int K, int u, const do
         }
         if (J < K) dmma2(acc1, pA1[J * 32], pB[J * 32]);
         tl2[r1 + K * 32] = l1;
-        dmma2(e1, l1, lk1);
         acc1.x += e1.x; acc1.y += e1.y;
         tl2[r1 + K * 32 + 32] = acc1;
         if (I == c) lfirst = l1;
     }
     if (u == 0 && c <= p.NB) {                                // pivot tile of stage K+2 (the S tile for c == NB)
         const double2* pA = tl2 + ltile(c, 0) * 32;
-        double2 acc = vd, e = make_double2(0.0, 0.0);
+        double2 acc = vd, e;
+        dmma2_z(e, lfirst, lfirst);
         int J = 0;
         for (; J + 1 < K; J += 2) {
             const double2 a0 = pA[J * 32], a1 = pA[J * 32 + 32];
@@ -257,7 +258,6 @@ __device__ __forceinline__ void stage_rows(const Prob& p, int K, int u, const do
             dmma(acc, a0.y, a0.y); dmma(e, a1.y, a1.y);
         }
         if (J < K) { const double2 a0 = pA[J * 32]; dmma2(acc, a0, a0); }
-        dmma2(e, lfirst, lfirst);
         acc.x += e.x; acc.y += e.y;
         p.Nd2[(c & 1) * 32] = acc;
     }
@@ -463,8 +463,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
                 if (flag[0]) { singular = true; break; }
                 const double2 w = Wt2[(K & 1) * 32 + lane];
                 const int rb = ltile(K + 1, 0);
-                double2 l = make_double2(0.0, 0.0);
-                dmma2(l, tl2[(rb + K) * 32], w);              // L(K+1,K) = N(K+1,K) (-W)'
+                double2 l;
+                dmma2_z(l, tl2[(rb + K) * 32], w);            // L(K+1,K) = N(K+1,K) (-W)'
                 double2 nd = Nd2[((K + 1) & 1) * 32 + lane];  // -V + sum_{J<K} L(K+1,J) L(K+1,J)'
                 dmma2(nd, l, l);
                 D.x = -nd.x; D.y = -nd.y;                     // D_{K+1}; for K+1 == NB this is -S
@@ -497,8 +497,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
                 if (flag[0]) break;
                 if (c <= NB) {
                     const double2 negW = Wt2[(K & 1) * 32 + lane];
-                    double2 lk1 = make_double2(0.0, 0.0);
-                    dmma2(lk1, tl2[(ltile(K + 1, 0) + K) * 32], negW);     // L(K+1,K), recomputed by every worker
+                    double2 lk1;
+                    dmma2_z(lk1, tl2[(ltile(K + 1, 0) + K) * 32], negW);   // L(K+1,K), recomputed by every worker
                     stage_rows<NW>(p, K, u, negW, lk1, vd);
                     t_x += KCLK() - tb1;
                 }

@@ -256,6 +256,17 @@ __device__ __forceinline__ void dmma(double2& c, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
         : "+d"(c.x), "+d"(c.y) : "d"(a), "d"(b));
 }
+// c = a * b with a zero accumulator: ptxas encodes the constant as RZ, so no register pair has to be zeroed first
+__device__ __forceinline__ void dmma_z(double2& c, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+        : "=d"(c.x), "=d"(c.y) : "d"(a), "d"(b), "d"(0.0), "d"(0.0));
+}
+// c = X * Y' (no accumulator input)
+__device__ __forceinline__ void dmma2_z(double2& c, const double2& x, const double2& y) {
+    dmma_z(c, x.x, y.x);
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c.x), "+d"(c.y) : "d"(x.y), "d"(y.y));
+}
 // c += X * Y' for two 8x8 tiles in C-fragment layout (even columns, then odd columns)
 __device__ __forceinline__ void dmma2(double2& c, const double2& x, const double2& y) {
     dmma(c, x.x, y.x);

@@ -49,3 +49,17 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+
+
+def test_header_is_plain_c():
+    """include/twxi.h is the C ABI: it must compile as C (no C++ constructs, no CUDA / torch types)."""
+    import shutil
+    import subprocess
+    import pytest
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = '#include "twxi.h"\nint main(void) { twxi_points p; p.npts = 0; return (int)sizeof(p) * 0 + TWXI_OK; }\n'
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
+                        "-x", "c", "-"], input=src, text=True, capture_output=True)
+    assert r.returncode == 0, r.stderr

@@ -238,6 +238,14 @@ def test_grid_knn_candidate_pruning_is_exact(env, monkeypatch):
     assert (pruned["status"] == 255).sum() == 4 * 83 + 60 - 4
     for k in ("tmin", "tmax", "tmin_norm", "tmax_norm", "tmin_se", "tmax_se", "ninvalid", "status"):
         assert np.array_equal(pruned[k], full[k]), k
+    # candidate lists that overflow their capacity: those blocks are searched over the whole table by the second launch
+    # (knn_kernel mode 1); 230 entries overflow some blocks of this chunk and not others, 64 overflows all of them
+    for cap in ("230", "64"):
+        monkeypatch.setenv("TWXI_KNN_CAP", cap)
+        capped = interp_chunk(ctx[0], ctx[1], wrk)
+        monkeypatch.delenv("TWXI_KNN_CAP")
+        for k in ("tmin", "tmax", "tmin_norm", "tmax_norm", "tmin_se", "tmax_se", "ninvalid", "status"):
+            assert np.array_equal(capped[k], full[k]), (cap, k)
 
 
 def test_xval_tair_anom_class(env):

@@ -39,7 +39,9 @@ struct KnnArgs {
     // guaranteed to contain the k1 nearest stations of every cell of the block (null = scan the whole table)
     const int32_t* cand;       // [nblocks][cand_cap]
     const int32_t* cand_cnt;   // [nblocks]; < 0: no list for this block, scan the whole table
-    int cand_cap, gx, nbx;
+    int cand_cap, gx, nbx, gy;
+    int ntab;                  // capacity of the shared-memory key table
+    int mode;                  // knn_kernel: 0 = CTA per query, 1 = CTA per block of cells with an overflowed candidate list
 };
 
 constexpr int KNN_BLK = 25;    // cells per side of a candidate block (the 250 x 250 tiles divide evenly)
@@ -67,16 +69,16 @@ __device__ void bitonic_sort(unsigned long long* key, int* idx, int P) {
     }
 }
 
-__global__ void __launch_bounds__(KNN_THREADS) knn_kernel(KnnArgs a) {
-    extern __shared__ unsigned long long smem_u64[];
-    unsigned long long* keys = smem_u64;                       // [n]
-    unsigned long long* selkey = keys + a.n;                   // [KNN_SEL]
+// One query point, by the whole CTA (every thread calls it with the same q).  `smem_u64`: key table of a.ntab entries, then
+// the selection arrays.
+__device__ void knn_query(const KnnArgs& a, const int q, unsigned long long* smem_u64) {
+    unsigned long long* keys = smem_u64;                       // [ntab]
+    unsigned long long* selkey = keys + a.ntab;                // [KNN_SEL]
     int* selidx = reinterpret_cast<int*>(selkey + KNN_SEL);    // [KNN_SEL]
     unsigned* hist = reinterpret_cast<unsigned*>(selidx + KNN_SEL);   // [256]
     __shared__ unsigned long long s_prefix;
     __shared__ unsigned s_remaining, s_bincount, s_cnt;
 
-    const int q = blockIdx.x;
     const int tid = threadIdx.x;
     const int k1 = a.k1;
     if (a.status[q] != TWXI_ST_OK) return;                     // masked cell / earlier failure
@@ -254,6 +256,32 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(KnnArgs a) {
     }
 }
 
+// mode 0: one CTA per query point; with candidate lists the key table holds a list (a.ntab = list capacity, a few KB: six
+//         CTAs per SM instead of two at 10 000 stations) and cells of blocks whose list overflowed are left to mode 1.
+// mode 1: one CTA per block of cells; only blocks whose candidate list overflowed do anything: their cells are searched
+//         over the whole station table (a.ntab = a.n).
+__global__ void __launch_bounds__(KNN_THREADS) knn_kernel(KnnArgs a) {
+    extern __shared__ unsigned long long smem_u64[];
+    if (a.mode == 0) {
+        const int q = blockIdx.x;
+        if (a.cand) {
+            const int b = (q / a.gx / KNN_BLK) * a.nbx + (q % a.gx) / KNN_BLK;
+            if (a.cand_cnt[b] < 0) return;
+        }
+        knn_query(a, q, smem_u64);
+    } else {
+        const int b = blockIdx.x;
+        if (a.cand_cnt[b] >= 0) return;
+        const int y0 = (b / a.nbx) * KNN_BLK, x0 = (b % a.nbx) * KNN_BLK;
+        const int y1 = min(y0 + KNN_BLK, a.gy), x1 = min(x0 + KNN_BLK, a.gx);
+        for (int y = y0; y < y1; ++y)
+            for (int x = x0; x < x1; ++x) {
+                knn_query(a, y * a.gx + x, smem_u64);
+                __syncthreads();                               // the next query reuses the shared tables
+            }
+    }
+}
+
 // Candidate stations of one block of grid cells.  With c the block's centre cell, r_c the distance of its k1-th
 // nearest station and delta the largest distance from c to a cell of the block, the triangle inequality puts the
 // k1 nearest stations of every cell within r_c + 2 delta of c.  The list is a superset, so the per-cell search over it
@@ -395,13 +423,16 @@ int launch_knn(Ctx& c, int npts, const double* lat, const double* lon, const int
     a.n = c.n; a.latrad = c.st.latrad; a.lonrad = c.st.lonrad; a.coslat = c.st.coslat;
     a.qlat = lat; a.qlon = lon; a.rm_idx = rm_idx; a.n_rm = rm_idx ? n_rm : 0; a.rm_zero = rm_zero; a.k1 = k1;
     a.out_idx = idx; a.out_dist = dist; a.out_wgt = wgt; a.status = status;
-    a.cand = nullptr; a.cand_cnt = nullptr; a.cand_cap = 0; a.gx = 0; a.nbx = 0;
+    a.cand = nullptr; a.cand_cnt = nullptr; a.cand_cap = 0; a.gx = 0; a.nbx = 0; a.gy = 0;
+    a.ntab = c.n; a.mode = 0;
+    int nblocks = 0;
     // gridded queries without leave-outs: prune the station table once per block of cells
     if (gy > 0 && gx > 0 && (long long)gy * gx == npts && a.n_rm == 0 && !rm_zero && c.n > 2 * k1 && !getenv("TWXI_KNN_FULL")) {
         if (!c.knn) c.knn = new KnnWork();
         KnnWork& w = *c.knn;
         const int nby = (gy + KNN_BLK - 1) / KNN_BLK, nbx = (gx + KNN_BLK - 1) / KNN_BLK;
-        const int cap = std::min(c.n, KNN_CAND_CAP);
+        int cap = std::min(c.n, KNN_CAND_CAP);
+        if (const char* e = getenv("TWXI_KNN_CAP")) cap = std::max(32, std::min(cap, atoi(e)));      // tests: force list overflow
         const size_t need = (size_t)nby * nbx * cap;
         if (need > w.cand_elems) {
             if (w.cand) cudaFree(w.cand);
@@ -415,7 +446,8 @@ int launch_knn(Ctx& c, int npts, const double* lat, const double* lon, const int
             TWXI_CUDA(cudaMalloc((void**)&w.cnt, (size_t)nby * nbx * sizeof(int32_t)));
             w.cnt_elems = (size_t)nby * nbx;
         }
-        a.cand_cap = cap; a.gx = gx; a.nbx = nbx;
+        a.cand_cap = cap; a.gx = gx; a.nbx = nbx; a.gy = gy;
+        nblocks = nby * nbx;
         const size_t smem_c = (size_t)c.n * 8 + 256 * 4;
         TWXI_CUDA(cudaFuncSetAttribute(knn_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
         knn_candidates_kernel<<<nby * nbx, KNN_THREADS, smem_c, c.stream>>>(a, gy, w.cand, w.cnt);
@@ -423,10 +455,19 @@ int launch_knn(Ctx& c, int npts, const double* lat, const double* lon, const int
         a.cand = w.cand; a.cand_cnt = w.cnt;
         w.last_blocks = nby * nbx;
     }
-    size_t smem = (size_t)c.n * 8 + KNN_SEL * 12 + 256 * 4;
-    TWXI_CUDA(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    knn_kernel<<<npts, KNN_THREADS, smem, c.stream>>>(a);
-    TWXI_LAUNCH_CHECK();
+    const size_t smem_full = (size_t)c.n * 8 + KNN_SEL * 12 + 256 * 4;
+    TWXI_CUDA(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_full));
+    if (a.cand) {
+        a.ntab = a.cand_cap;                                   // per-cell search over the block's list
+        knn_kernel<<<npts, KNN_THREADS, (size_t)a.ntab * 8 + KNN_SEL * 12 + 256 * 4, c.stream>>>(a);
+        TWXI_LAUNCH_CHECK();
+        a.ntab = c.n; a.mode = 1;                              // blocks whose list overflowed: whole table (normally none)
+        knn_kernel<<<nblocks, KNN_THREADS, smem_full, c.stream>>>(a);
+        TWXI_LAUNCH_CHECK();
+    } else {
+        knn_kernel<<<npts, KNN_THREADS, smem_full, c.stream>>>(a);
+        TWXI_LAUNCH_CHECK();
+    }
     return TWXI_OK;
 }
 

@@ -303,3 +303,30 @@ def test_variogram_fit_and_krig_all_vs_oracle(env):
             assert abs(got[2] - rng) <= 1e-5 * max(abs(rng), 1e-3), (sid, m, got, (nug, psill, rng))
     nugs, psills, rngs = kp.get_krig_params(sids[2])
     assert np.array_equal(nugs, v[2, :, 0]) and np.array_equal(rngs, v[2, :, 2])
+
+
+def test_interp_to_lonlat_from_predictor_rasters(env, tmp_path):
+    """PtInterpTair.interp_to_lonlat (interp_tair.py:513-524): predictors looked up in the rasters of a PredictorStore; the
+    result equals the chunk result of the cell that contains the point, and a masked cell raises like the reference."""
+    from topowx_b200.context import interp_chunk
+    from topowx_b200.interp import PtInterpTair, PredictorStore
+    synth, db = env["synth"], env["db"]
+    r0, c0 = synth.TILE_ROW0 + 100, synth.TILE_COL0 + 100
+    store = PredictorStore.create_synthetic(str(tmp_path / "rasters"), env["f"], r0, c0, 12, 16)
+    pti = PtInterpTair(env["da"][0], env["da"][1], aux_fpaths=store)
+    wrk = synth.make_wrk_chk_grid(env["f"], r0, c0, 12, 16)
+    wrk[2, 3, 4] = 0                                                   # one cell taken out of the chunk's mask
+    out = interp_chunk(pti.ctx_tmin, pti.ctx_tmax, wrk)
+    lon, lat = synth.grid_lons(c0 + 9) + 0.002, synth.grid_lats(r0 + 5) - 0.003
+    tmin_dly, tmax_dly, tmin_norms, tmax_norms, tmin_se, tmax_se, ninvalid = pti.interp_to_lonlat(lon, lat)
+    assert pti.a_pt[db.LON] == synth.grid_lons(c0 + 9) and pti.a_pt[db.LAT] == synth.grid_lats(r0 + 5)
+    assert np.abs(tmin_norms - out["tmin_norm"][:, 5, 9]).max() < 1e-6
+    assert np.abs(tmax_se - out["tmax_se"][:, 5, 9]).max() < 1e-6
+    scale = 0.01
+    assert np.abs(tmin_dly - out["tmin"][:, 5, 9] * scale).max() <= 0.0051
+    assert ninvalid == out["ninvalid"][5, 9]
+    mask = np.array(pti.pGrids.rasters["mask"])                        # the store's rasters are read-only maps
+    mask[3, 4] = 0
+    pti.pGrids.rasters["mask"] = mask
+    with pytest.raises(Exception, match="outside interpolation region"):
+        pti.interp_to_lonlat(synth.grid_lons(c0 + 4), synth.grid_lats(r0 + 3))

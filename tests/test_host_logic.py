@@ -234,3 +234,30 @@ def test_station_data_wrk_chk_cache():
     got = wc.load_obs(np.concatenate([inside, far]), mth=7)
     assert wc.chk_deg_buf > 1 and got.shape == (31, 5)
     np.testing.assert_array_equal(got, da.load_obs(np.sort(np.concatenate([inside, far])), mth=7))
+
+
+def test_predictor_grids_lookup(tmp_path):
+    """PredictorGrids.setPtValues (interp_tair.py:87-141) over a PredictorStore: order 0 = value of the containing cell and the
+    point moved to the cell centre; order 1 = bilinear."""
+    from topowx_b200 import synth, db
+    from topowx_b200.interp import PredictorStore, PredictorGrids
+    from topowx_b200.interp.interp_tair import build_empty_pt
+    f = synth.Fields()
+    store = PredictorStore.create_synthetic(str(tmp_path / "r"), f, 1000, 3000, 30, 40)
+    pg = PredictorGrids(store, interpOrders={"elev": 1})
+    ref = synth.make_wrk_chk_grid(f, 1000, 3000, 30, 40)
+    pt = build_empty_pt()
+    lat_c, lon_c = synth.grid_lats(1012), synth.grid_lons(3025)
+    pt[db.LON], pt[db.LAT] = lon_c + 0.003, lat_c - 0.002             # inside cell (12, 25)
+    pg.setPtValues(pt, chgLatLon=True)
+    assert pt[db.LON] == lon_c and pt[db.LAT] == lat_c
+    assert pt[db.ELEV] == ref[5, 12, 25] and pt[db.TDI] == ref[6, 12, 25] and pt[db.CLIMDIV] == ref[7, 12, 25]
+    assert pt["tmin03"] == ref[8 + 2, 12, 25] and pt["tmax11"] == ref[20 + 10, 12, 25] and pt[db.MASK] == ref[2, 12, 25]
+    pt[db.LON], pt[db.LAT] = lon_c + 0.5 * synth.RES, lat_c           # half way to the next column, order 1
+    pg.setPtValues(pt, chgLatLon=False)
+    assert abs(pt[db.ELEV] - 0.5 * (ref[5, 12, 25] + ref[5, 12, 26])) < 1e-9
+    assert pt[db.TDI] in (ref[6, 12, 25], ref[6, 12, 26])
+    import pytest
+    pt[db.LON] = lon_c + 10.0
+    with pytest.raises(Exception):
+        pg.setPtValues(pt)

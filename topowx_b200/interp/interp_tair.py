@@ -4,12 +4,13 @@ Classes and functions for performing Tair interpolation: the `twx.interp.interp_
 
 Kept, with the reference's signatures: KrigTair, GwrTairAnom, InterpTair, PtInterpTair, StationDataWrkChk,
 build_empty_pt (tmin_tmax_fixer runs inside the CUDA library: twxi_interp_cells / twxi_interp_chunk).  New batch entry points (no reference equivalent): InterpTair.interp_batch,
-PtInterpTair.interp_chunk.  Not rebuilt (out of the hot path): KrigTairAll,
-BuildKrigParams (variogram fitting in R/gstat), PredictorGrids / interp_to_lonlat (raster I/O), GwrTairAnomR,
-GwrTairNorm.
+PtInterpTair.interp_chunk.  KrigTairAll / BuildKrigParams run the variogram fitting of R get_vario_params as a CUDA
+kernel; PredictorGrids / interp_to_lonlat read the rasters of a PredictorStore.  Not rebuilt: GwrTairAnomR, GwrTairNorm
+(dead code in the reference).
 '''
 
-__all__ = ["GwrTairAnom", 'KrigTair', 'KrigTairAll', 'BuildKrigParams', 'InterpTair', 'StationDataWrkChk', 'PtInterpTair']
+__all__ = ["GwrTairAnom", 'KrigTair', 'KrigTairAll', 'BuildKrigParams', 'InterpTair', 'StationDataWrkChk', 'PtInterpTair',
+           'PredictorGrids']
 
 import numpy as np
 
@@ -55,6 +56,61 @@ def build_empty_pt():
     ptDtype.extend([(get_optim_anom_varname(mth), np.float64) for mth in np.arange(1, 13)])
     a_pt = np.empty(1, dtype=ptDtype)
     return a_pt[0]
+
+
+class PredictorGrids(object):
+    '''
+    Auxiliary predictor values of a point from the predictor rasters (interp_tair.py:87-141).  The reference opens one
+    netCDF file per predictor; here the rasters are a `PredictorStore` (topowx_b200/interp/feed.py: .npy rasters, or the
+    path of such a directory).  Order 0 (default) takes the value of the grid cell that contains the point and, with
+    chgLatLon, moves the point to the cell centre; order 1 interpolates bilinearly and falls back to the nearest cell where
+    a corner is missing (the bm.interp(order=1) -> order=0 fallback of :131-139).
+    '''
+    PT_FIELD = {'elev': ELEV, 'tdi': TDI, 'climdiv': CLIMDIV, 'mask': MASK}
+
+    def __init__(self, store, interpOrders=None):
+        from .feed import PredictorStore, PLANE_NAMES
+        self.store = store if isinstance(store, PredictorStore) else PredictorStore(store)
+        self.names = ['mask'] + list(PLANE_NAMES)
+        self.rasters = dict(zip(PLANE_NAMES, self.store.rasters))
+        self.rasters['mask'] = self.store.variables['mask']
+        orders = {} if interpOrders is None else dict(interpOrders)
+        self.orders = {n: int(orders.get(n, 0)) for n in self.names}
+        self.lons = np.asarray(self.store.variables['lon'], dtype=np.float64)
+        self.lats = np.asarray(self.store.variables['lat'], dtype=np.float64)          # descending
+        self.dx = float(self.lons[1] - self.lons[0])
+        self.dy = float(self.lats[0] - self.lats[1])
+
+    def get_row_col(self, lon, lat):
+        col = int(np.floor((lon - (self.lons[0] - 0.5 * self.dx)) / self.dx))
+        row = int(np.floor(((self.lats[0] + 0.5 * self.dy) - lat) / self.dy))
+        if not (0 <= row < self.lats.size and 0 <= col < self.lons.size):
+            raise Exception("Lon/Lat outside the bounds of the predictor grids")      # GeoNc.get_row_col
+        return row, col, float(self.lons[col]), float(self.lats[row])
+
+    def _bilinear(self, a, lon, lat):
+        fx = (lon - self.lons[0]) / self.dx
+        fy = (self.lats[0] - lat) / self.dy
+        c0, r0 = int(np.floor(fx)), int(np.floor(fy))
+        if not (0 <= r0 < self.lats.size - 1 and 0 <= c0 < self.lons.size - 1):
+            return np.nan
+        tx, ty = fx - c0, fy - r0
+        v = np.asarray(a[r0:r0 + 2, c0:c0 + 2], dtype=np.float64)
+        return float((1 - ty) * ((1 - tx) * v[0, 0] + tx * v[0, 1]) + ty * ((1 - tx) * v[1, 0] + tx * v[1, 1]))
+
+    def setPtValues(self, aPt, chgLatLon=True):
+        row, col, gridlon, gridlat = self.get_row_col(float(aPt[LON]), float(aPt[LAT]))
+        for n in self.names:
+            field = self.PT_FIELD.get(n, n)
+            if self.orders[n] == 1 and not chgLatLon:
+                v = self._bilinear(self.rasters[n], float(aPt[LON]), float(aPt[LAT]))
+                if not np.isfinite(v):
+                    v = float(self.rasters[n][row, col])
+            else:
+                v = float(self.rasters[n][row, col])
+            aPt[field] = v
+        if chgLatLon:
+            aPt[LON], aPt[LAT] = gridlon, gridlat
 
 
 class GwrTairAnom(object):
@@ -210,14 +266,26 @@ class PtInterpTair(object):
         self.ctx_tmin = stn_slct_tmin.ctx
         self.ctx_tmax = stn_slct_tmax.ctx
         self.norms_only = norms_only
-        if aux_fpaths is not None:
-            raise NotImplementedError("PredictorGrids / interp_to_lonlat read predictor rasters with netCDF4 + "
-                                      "basemap (interp_tair.py:87-141); raster I/O stays on the reference path")
+        self.pGrids = None
+        if aux_fpaths is not None:                                 # a PredictorStore or the path of one (feed.py)
+            self.pGrids = PredictorGrids(aux_fpaths, interp_orders)
         self.a_pt = build_empty_pt()
 
     def interp_to_lonlat(self, lon, lat, fixInvalid=True, chgLatLon=True, stns_rm=None, elev=None):
-        raise NotImplementedError("raster predictor lookup (PredictorGrids) stays on the reference path; fill "
-                                  "PtInterpTair.a_pt and call interp_pt()")
+        '''
+        Interpolate Tmin and Tmax to a lon/lat; the auxiliary predictors come from the predictor rasters
+        (interp_tair.py:513-524).  Returns the 7-tuple of interp_pt.
+        '''
+        if self.pGrids is None:
+            raise Exception("PtInterpTair was built without predictor rasters (aux_fpaths)")
+        self.a_pt[LON] = lon
+        self.a_pt[LAT] = lat
+        self.pGrids.setPtValues(self.a_pt, chgLatLon)
+        if elev is not None:
+            self.a_pt[ELEV] = elev
+        if self.a_pt[MASK] == 0:
+            raise Exception('Point is outside interpolation region')
+        return self.interp_pt(fixInvalid, stns_rm)
 
     def interp_pt(self, fix_invalid=True, stns_rm=None):
         '''

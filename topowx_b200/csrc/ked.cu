@@ -26,7 +26,7 @@
 //     Data flow per problem (N := sum L L' - V, the negated Schur complement, so DMMAs accumulate in place):
 //       prologue   one thread issues a TMA bulk copy (cp.async.bulk + mbarrier) per tile row that lands the raw
 //                  distance tiles straight in the shared-memory slots of L; meanwhile all warps build B'; then one
-//                  pass turns every slot into -C(h) (ked_common.cuh: cov_pos).
+//                  pass turns every slot into -C(h) (ked_common.cuh: ncov_pos).
 //       stage K    diagonal warp: -W = -inv(chol(D_K))' (chol8_inverse_t: fraction-free elimination of the pivot tile
 //                  as DMMA outer products), publish it; ONE CTA barrier; then it forms L(K+1,K) and D_{K+1} itself
 //                  and goes on factoring while the workers are busy with stage K.
@@ -44,7 +44,7 @@
 
 namespace twxi {
 
-constexpr int KED_HDR = 8 + 64 + 2 * 128;         // doubles: flag + mbarrier, 2^(j/64), -inv(L_KK) x2, N_diag x2
+constexpr int KED_HDR = 8 + KED_TABN + 2 * 128;         // doubles: flag + mbarrier, 2^(j/64), -inv(L_KK) x2, N_diag x2
 
 // ---- 1. compact distance tiles -------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) hgather_kernel(StnTable st, int q0, int nq, int k1, const int32_t* idx,
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) hgather_kernel(StnTable st, int q0, int n
         CovPar cp;
         covpar_set(cp, vp[0], vp[1], vp[2]);
         double* c = out + off_cp + m * 8;
-        c[0] = cp.c00; c[1] = cp.nir; c[2] = cp.nk; c[3] = cp.c0; c[4] = cp.c2; c[5] = cp.c3; c[6] = cp.c4; c[7] = cp.c5;
+        c[0] = cp.c00; c[1] = cp.nk; c[2] = cp.c0; c[3] = cp.c1; c[4] = cp.c2; c[5] = cp.c3; c[6] = cp.c4; c[7] = cp.c5;
     }
     for (int I = 0; I < NB; ++I) {
         const int cnt = (I + 1) * 64;
@@ -178,8 +178,7 @@ struct Prob {
 // -V(c,c) of a diagonal tile from its raw distances (zero for the S tile c == NB)
 __device__ __forceinline__ double2 neg_cov_diag(const Prob& p, int c, double2 hd) {
     if (c >= p.NB) return make_double2(0.0, 0.0);
-    const double2 v = cov_tile(hd, 8 * c + p.r8, 8 * c + 2 * p.q4, p.n, p.cp, p.tab32, false);
-    return make_double2(-v.x, -v.y);
+    return ncov_tile(hd, 8 * c + p.r8, 8 * c + 2 * p.q4, p.n, p.cp, p.tab32, false);
 }
 
 // Stage K of a worker (rows I = K+2+u, K+2+u+NW, ..., two rows per pass: four independent DMMA chains):
@@ -277,9 +276,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
     extern __shared__ __align__(16) double sm[];
     int* flag = reinterpret_cast<int*>(sm);                   // [0] singular
     void* mbar = sm + 2;                                      // mbarrier of the distance-tile bulk copies
-    double* tab32 = sm + 8;                                   // 64: 2^(j/64)
-    double2* Wt2 = reinterpret_cast<double2*>(sm + 72);       // 2 x 64: -inv(L_KK), double-buffered by K & 1
-    double2* Nd2 = reinterpret_cast<double2*>(sm + 200);      // 2 x 64: N_diag of column c, double-buffered by c & 1
+    double* tab32 = sm + 8;                                   // KED_TABN: 2^(j/KED_TABN)
+    double2* Wt2 = reinterpret_cast<double2*>(sm + 8 + KED_TABN);          // 2 x 64: -inv(L_KK), double-buffered by K & 1
+    double2* Nd2 = reinterpret_cast<double2*>(sm + 8 + KED_TABN + 128);    // 2 x 64: N_diag of column c, double-buffered by c & 1
     double* tiles = sm + KED_HDR;
     constexpr int NT = (NW + 1) * 32;
     constexpr int NJ = (NMAX + NT - 1) / NT;                  // stations per thread in the B' build (n <= NMAX)
@@ -364,7 +363,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
             if (NB > 1) hd1 = p.hc2[htile(1, 1) * 32];
         }
         if (warp == NW - 1 && NB > 2) hd = p.hc2[htile(2, 2) * 32];     // look-ahead worker (u == 0)
-        p.cp.c00 = cp0.x; p.cp.nir = cp0.y; p.cp.nk = cp1.x; p.cp.c0 = cp1.y;
+        p.cp.c00 = cp0.x; p.cp.nk = cp0.y; p.cp.c0 = cp1.x; p.cp.c1 = cp1.y;
         p.cp.c2 = cp2.x; p.cp.c3 = cp2.y; p.cp.c4 = cp3.x; p.cp.c5 = cp3.y;
         if (warp == NW && pending) {
             ked_finish(a.mean, a.var, a.status, pend_S, pend_q, pend_m, pend_yref, pend_c00, lane);
@@ -384,7 +383,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
                     col[24] = in ? (elev0 - gl[t][2]) * 1e-3 : 0.0;
                     col[32] = in ? (lst0 - gl[t][3]) * 0.1 : 0.0;
                     col[40] = in ? yref - gl[t][4] : 0.0;
-                    col[48] = in ? -cov(gl[t][5], p.cp, tab32) : 0.0;
+                    col[48] = in ? ncov(gl[t][5], p.cp, tab32) : 0.0;
                     col[56] = 0.0;
                 }
             }
@@ -410,18 +409,17 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
             for (; t + 3 * NWT < T0; t += 4 * NWT) {
                 const double2 h1 = tl2[t * 32], h2 = tl2[(t + NWT) * 32], h3 = tl2[(t + 2 * NWT) * 32], h4 = tl2[(t + 3 * NWT) * 32];
                 double2 v1, v2, v3, v4;
-                v1.x = -cov_pos(h1.x, p.cp, tab32); v2.x = -cov_pos(h2.x, p.cp, tab32); v3.x = -cov_pos(h3.x, p.cp, tab32); v4.x = -cov_pos(h4.x, p.cp, tab32);
-                v1.y = -cov_pos(h1.y, p.cp, tab32); v2.y = -cov_pos(h2.y, p.cp, tab32); v3.y = -cov_pos(h3.y, p.cp, tab32); v4.y = -cov_pos(h4.y, p.cp, tab32);
+                v1.x = ncov_pos(h1.x, p.cp, tab32); v2.x = ncov_pos(h2.x, p.cp, tab32); v3.x = ncov_pos(h3.x, p.cp, tab32); v4.x = ncov_pos(h4.x, p.cp, tab32);
+                v1.y = ncov_pos(h1.y, p.cp, tab32); v2.y = ncov_pos(h2.y, p.cp, tab32); v3.y = ncov_pos(h3.y, p.cp, tab32); v4.y = ncov_pos(h4.y, p.cp, tab32);
                 tl2[t * 32] = v1; tl2[(t + NWT) * 32] = v2; tl2[(t + 2 * NWT) * 32] = v3; tl2[(t + 3 * NWT) * 32] = v4;
             }
             for (; t < T0; t += NWT) {
                 const double2 h1 = tl2[t * 32];
-                tl2[t * 32] = make_double2(-cov_pos(h1.x, p.cp, tab32), -cov_pos(h1.y, p.cp, tab32));
+                tl2[t * 32] = make_double2(ncov_pos(h1.x, p.cp, tab32), ncov_pos(h1.y, p.cp, tab32));
             }
             const bool plain = 8 * NB <= n;                   // last row of V: identity padding beyond n
             for (int c = warp; c < NB - 1; c += NW + 1) {
-                const double2 v = cov_tile(tl2[(T0 + c) * 32], 8 * (NB - 1) + p.r8, 8 * c + 2 * p.q4, n, p.cp, tab32, plain);
-                tl2[(T0 + c) * 32] = make_double2(-v.x, -v.y);
+                tl2[(T0 + c) * 32] = ncov_tile(tl2[(T0 + c) * 32], 8 * (NB - 1) + p.r8, 8 * c + 2 * p.q4, n, p.cp, tab32, plain);
             }
             if (warp == NW) {
                 p.Nd2[0] = neg_cov_diag(p, 0, hd);

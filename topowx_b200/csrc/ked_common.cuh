@@ -44,15 +44,24 @@ __device__ __forceinline__ int htile(int I, int J) { return I * (I + 1) / 2 + J;
 
 
 // ---- covariances, barrier / bulk-copy helpers, the 5x5 GLS --------------------------------------------------------
-// Covariances.  psill * exp(-h / range) for h >= 0 with ~1e-16 relative error: with t = -h / range,
-// t = k ln2/64 + r (|r| <= ln2/128), exp(t) = 2^(k >> 6) * 2^((k & 63)/64) * P5(r); psill is folded into the
-// coefficients of P5, the power-of-two table lives in shared memory.  Branch-free: 10 FP64 operations, one table
-// lookup and five integer operations per value (this is a third of all the instructions of the kriging kernel).
-constexpr int KED_TABN = 64;
+// Covariances.  -psill * exp(-h / range) for h >= 0 with ~1e-16 relative error: with u = -h T / (range ln2),
+// k = rint(u), f = u - k (|f| <= 1/2, exact: the product lives inside one fma), exp(-h/range) = 2^(k / T) * exp(f ln2 / T)
+// = 2^(k div T) * tab[k mod T] * P(f); -psill and the powers of ln2 / T are folded into the coefficients of P, the table
+// 2^(j/T) lives in shared memory.  Branch-free: 3 + KED_COVDEG + 1 FP64 operations, one table lookup and four integer
+// operations per value (T = 64: degree 5, truncation 6e-18; T = 256: degree 4, 4e-17; T = 1024: degree 3, 5e-16).
+// The kernel works on -V throughout, hence the sign.  T = 64 is the measured optimum (profiles/covtab_r02.txt): the
+// larger tables save an FMA each but cost resident CTAs in the heavy size classes.
+#ifndef TWXI_COV_TAB
+#define TWXI_COV_TAB 64
+#endif
+constexpr int KED_TABN = TWXI_COV_TAB;
+constexpr int KED_TABLOG = KED_TABN == 64 ? 6 : KED_TABN == 256 ? 8 : 10;
+constexpr int KED_COVDEG = KED_TABN == 64 ? 5 : KED_TABN == 256 ? 4 : 3;
+static_assert(KED_TABN == 64 || KED_TABN == 256 || KED_TABN == 1024, "TWXI_COV_TAB must be 64, 256 or 1024");
 struct CovPar {
     double c00;                      // C(0) = nugget + partial sill
-    double nir, nk;                  // -1/range and -64/(range ln2); 0 for the pure nugget model
-    double c0, c2, c3, c4, c5;       // psill * {1, 1/2, 1/6, 1/24, 1/120} (0 for the pure nugget model)
+    double nk;                       // -T / (range ln2); 0 for the pure nugget model
+    double c0, c1, c2, c3, c4, c5;   // -psill * (ln2/T)^j / j! (0 for the pure nugget model)
 };
 __device__ __forceinline__ void covpar_set(CovPar& cp, double nug, double psill, double rng) {
     cp.c00 = nug + psill;
@@ -60,49 +69,51 @@ __device__ __forceinline__ void covpar_set(CovPar& cp, double nug, double psill,
     // 4 m: every covariance between distinct stations is already zero) so that k stays inside 32 bits.
     const bool nugget_only = !(rng != 0.0) || !(psill != 0.0);
     const double nir = nugget_only ? 0.0 : fmax(-1.0 / rng, -250.0);
-    const double ps = nugget_only ? 0.0 : psill;
-    cp.nir = nir;
-    cp.nk = nir * 92.33248261689366;                          // 64 / ln2
-    cp.c0 = ps; cp.c2 = ps * 0.5; cp.c3 = ps * (1.0 / 6.0); cp.c4 = ps * (1.0 / 24.0); cp.c5 = ps * (1.0 / 120.0);
+    const double ps = nugget_only ? 0.0 : -psill;
+    const double a = 0.6931471805599453 / KED_TABN;
+    cp.nk = nir * (KED_TABN * 1.4426950408889634);            // T / ln2
+    cp.c0 = ps; cp.c1 = ps * a; cp.c2 = ps * (a * a * 0.5); cp.c3 = ps * (a * a * a * (1.0 / 6.0));
+    cp.c4 = ps * (a * a * a * a * (1.0 / 24.0)); cp.c5 = ps * (a * a * a * a * a * (1.0 / 120.0));
 }
-// C(h) for h > 0 (also the value the exponential model takes at h == 0, without the nugget)
-__device__ __forceinline__ double cov_pos(double h, const CovPar& cp, const double* __restrict__ tab) {
+// -C(h) for h > 0 (also minus the value the exponential model takes at h == 0, without the nugget)
+__device__ __forceinline__ double ncov_pos(double h, const CovPar& cp, const double* __restrict__ tab) {
 #if TWXI_KED_FAKE == 2
-    return cp.c0 * (h * cp.nir);
+    return cp.c0 * (h * cp.nk);
 #else
     const double SHIFT = 6755399441055744.0;                  // 2^52 + 2^51: rounds to nearest integer
     double kd = fma(h, cp.nk, SHIFT);
     int ki = __double2loint(kd);
     kd -= SHIFT;
-    const double r = fma(kd, -0.010830424696249145, h * cp.nir);    // ln2/64; the product is exact inside the fma, and the
-                                                              // rounding of the constant costs |k| * 1.2e-18 (< 1e-15 for h < 12 ranges)
-    double p = fma(r, cp.c5, cp.c4);
-    p = fma(r, p, cp.c3);
-    p = fma(r, p, cp.c2);
-    p = fma(r, p, cp.c0);
-    p = fma(r, p, cp.c0);
-    ki = max(ki, -KED_TABN * 1000);                                // below 2^-1000 the value does not matter, the exponent must stay valid
+    const double f = fma(h, cp.nk, -kd);                      // exact
+    double p;
+    if (KED_COVDEG == 5) { p = fma(f, cp.c5, cp.c4); p = fma(f, p, cp.c3); }
+    else if (KED_COVDEG == 4) p = fma(f, cp.c4, cp.c3);
+    else p = cp.c3;
+    p = fma(f, p, cp.c2);
+    p = fma(f, p, cp.c1);
+    p = fma(f, p, cp.c0);
+    ki = max(ki, -KED_TABN * 1000);                           // below 2^-1000 the value does not matter, the exponent must stay valid
     const double v = p * tab[ki & (KED_TABN - 1)];
-    return __hiloint2double(__double2hiint(v) + ((ki >> 6) << 20), __double2loint(v));
+    return __hiloint2double(__double2hiint(v) + ((ki >> KED_TABLOG) << 20), __double2loint(v));
 #endif
 }
-// C(h) of a pair that may be co-located (point - station): nug+psill at h == 0
-__device__ __forceinline__ double cov(double h, const CovPar& cp, const double* tab) {
-    const double e = cov_pos(h, cp, tab);
-    return h == 0.0 ? cp.c00 : e;
+// -C(h) of a pair that may be co-located (point - station): -(nug+psill) at h == 0
+__device__ __forceinline__ double ncov(double h, const CovPar& cp, const double* tab) {
+    const double e = ncov_pos(h, cp, tab);
+    return h == 0.0 ? -cp.c00 : e;
 }
-// V tile (I, K) from its distance tile in C-fragment layout; lane holds (i, j) and (i, j+1).
+// -V tile (I, K) from its distance tile in C-fragment layout; lane holds (i, j) and (i, j+1).
 // `plain` (warp-uniform): the tile is strictly below the diagonal and inside the n x n block, so no masking.
-__device__ __forceinline__ double2 cov_tile(double2 h, int i, int j, int n, const CovPar& cp, const double* tab32,
-                                            bool plain) {
+__device__ __forceinline__ double2 ncov_tile(double2 h, int i, int j, int n, const CovPar& cp, const double* tab32,
+                                             bool plain) {
     double2 v;                                                // (co-located station pairs never get here: hgather)
-    v.x = cov_pos(h.x, cp, tab32);
-    v.y = cov_pos(h.y, cp, tab32);
+    v.x = ncov_pos(h.x, cp, tab32);
+    v.y = ncov_pos(h.y, cp, tab32);
     if (!plain) {                                             // diagonal tiles are kept fully symmetric (elim8_mma)
-        if (j == i) v.x = cp.c00;
-        if (j + 1 == i) v.y = cp.c00;
-        if (i >= n || j >= n) v.x = (i == j) ? 1.0 : 0.0;     // identity padding
-        if (i >= n || j + 1 >= n) v.y = (i == j + 1) ? 1.0 : 0.0;
+        if (j == i) v.x = -cp.c00;
+        if (j + 1 == i) v.y = -cp.c00;
+        if (i >= n || j >= n) v.x = (i == j) ? -1.0 : 0.0;    // identity padding
+        if (i >= n || j + 1 >= n) v.y = (i == j + 1) ? -1.0 : 0.0;
     }
     return v;
 }

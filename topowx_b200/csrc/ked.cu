@@ -292,6 +292,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
     for (int i = tid; i < KED_TABN; i += NT) tab32[i] = exp2((double)i / KED_TABN);
     if (tid == 0) mbar_init(mbar, 1);
     uint32_t parity = 0;
+    const long long lane_zero = (long long)(lane * a.zero);
 
     Prob p;
     p.tl2 = reinterpret_cast<double2*>(tiles) + lane;
@@ -364,7 +365,12 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
         }
         if (warp == NW - 1 && NB > 2) hd = p.hc2[htile(2, 2) * 32];     // look-ahead worker (u == 0)
         p.cp.c00 = cp0.x; p.cp.nk = cp0.y; p.cp.c0 = cp1.x; p.cp.c1 = cp1.y;
-        p.cp.c2 = cp2.x; p.cp.c3 = cp2.y; p.cp.c4 = cp3.x; p.cp.c5 = cp3.y;
+        p.cp.c2 = cp2.x; p.cp.c3 = cp2.y; p.cp.c4 = cp3.x;
+        // The parameters are warp-uniform and end up in uniform registers; an FP64 instruction takes one uniform / immediate
+        // operand, so fma(h, nk, SHIFT) and fma(f, c5, c4) each cost two extra register moves per value.  c5 and SHIFT are
+        // therefore made formally lane-dependent (lane * 0) and live in ordinary registers.
+        p.cp.c5 = __longlong_as_double(__double_as_longlong(cp3.y) + lane_zero);
+        p.cp.shift = __longlong_as_double(KED_SHIFT_BITS + lane_zero);
         if (warp == NW && pending) {
             ked_finish(a.mean, a.var, a.status, pend_S, pend_q, pend_m, pend_yref, pend_c00, lane);
             pending = false;
@@ -643,6 +649,7 @@ int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
     a.hc = w.hc; a.hc_stride = hc_stride; a.list = w.list; a.bstart = bstart; a.bcount = bcount;
     a.mean = b.mean; a.var = b.var; a.status = b.status;
     a.rot_sms = 0;
+    a.zero = 0;
     const int single = mth >= 1 ? mth - 1 : -1;
     for (int q0 = 0; q0 < b.npts; q0 += qcap) {
         const int nq = std::min(qcap, b.npts - q0);

@@ -30,6 +30,7 @@ struct KedArgs {
     const int32_t* bstart;     // [KED_MAXNB+1]
     const int32_t* bcount;
     int nbv;                   // size class of this launch
+    int zero;                  // always 0 (a value the compiler cannot fold: see ked_kernel, covariance operands)
     int rot_sms;               // > 0: warp roles rotate with blockIdx.x / rot_sms (the CTA's residency slot on its SM), so that
                                // the diagonal warps of the CTAs of one SM sit on different SM sub-partitions
     double* mean;              // [npts][12]
@@ -62,7 +63,9 @@ struct CovPar {
     double c00;                      // C(0) = nugget + partial sill
     double nk;                       // -T / (range ln2); 0 for the pure nugget model
     double c0, c1, c2, c3, c4, c5;   // -psill * (ln2/T)^j / j! (0 for the pure nugget model)
+    double shift;                    // 2^52 + 2^51 (adding it rounds to the nearest integer), kept in a register
 };
+constexpr long long KED_SHIFT_BITS = 0x4338000000000000ll;
 __device__ __forceinline__ void covpar_set(CovPar& cp, double nug, double psill, double rng) {
     cp.c00 = nug + psill;
     // range == 0: pure nugget model, C(h > 0) = 0 (interp.R:223-227).  -1/range is clamped at -250 / km (a range of
@@ -80,10 +83,9 @@ __device__ __forceinline__ double ncov_pos(double h, const CovPar& cp, const dou
 #if TWXI_KED_FAKE == 2
     return cp.c0 * (h * cp.nk);
 #else
-    const double SHIFT = 6755399441055744.0;                  // 2^52 + 2^51: rounds to nearest integer
-    double kd = fma(h, cp.nk, SHIFT);
+    double kd = fma(h, cp.nk, cp.shift);
     int ki = __double2loint(kd);
-    kd -= SHIFT;
+    kd -= cp.shift;
     const double f = fma(h, cp.nk, -kd);                      // exact
     double p;
     if (KED_COVDEG == 5) { p = fma(f, cp.c5, cp.c4); p = fma(f, p, cp.c3); }

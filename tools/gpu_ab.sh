@@ -6,5 +6,5 @@ for r in 1 2; do for v in "$@"; do
   TWXI_LIB=$PWD/topowx_b200/libtwxi$v.so TWXI_KED_CFG="lib$v" python tools/time_tile_c5.py 3 3 2>&1 | tail -1
 done; done | tee -a gpurun_out/ab.log
 for v in "$@"; do
-  TWXI_LIB=$PWD/topowx_b200/libtwxi$v.so python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py -x -q -m gpu -k "krig or full_tile or station" 2>&1 | tail -1
+  TWXI_LIB=$PWD/topowx_b200/libtwxi$v.so python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py -x -q -m gpu -k "krig or full_tile or station or gwr or chunk" 2>&1 | tail -1
 done | tee -a gpurun_out/ab.log

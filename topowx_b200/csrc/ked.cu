@@ -274,7 +274,8 @@ __device__ unsigned long long g_ked_prof[16];
 template <int NW, int MINB, int NMAX>
 __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
     extern __shared__ __align__(16) double sm[];
-    int* flag = reinterpret_cast<int*>(sm);                   // [0] singular
+    int* flag = reinterpret_cast<int*>(sm);                   // (profiling builds only)
+    (void)flag;
     void* mbar = sm + 2;                                      // mbarrier of the distance-tile bulk copies
     double* tab32 = sm + 8;                                   // KED_TABN: 2^(j/KED_TABN)
     double2* Wt2 = reinterpret_cast<double2*>(sm + 8 + KED_TABN);          // 2 x 64: -inv(L_KK), double-buffered by K & 1
@@ -330,7 +331,6 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
         __syncthreads();                                      // previous problem: shared memory fully consumed
         const long long tp1 = KCLK();
         if (tid == 0) {
-            flag[0] = 0;
             if (tx_bytes) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_expect_tx(mbar, tx_bytes);
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
 #if TWXI_KED_FAKE == 1
                 const bool ok = true; zt = D;
 #else
-                const bool ok = chol8_inverse_t(D, zt, lane);
+                const bool ok = chol8_inverse_ldl(D, zt, lane);
 #endif
                 t_x += KCLK() - tc0;
                 {   // publish -inv(L_KK) row-major: lane (c, q) holds Z[c][2q..2q+1] = W[2q..2q+1][c]
@@ -459,12 +459,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
                     Wd[16 * p.q4 + p.r8] = -zt.x;
                     Wd[16 * p.q4 + 8 + p.r8] = -zt.y;
                 }
-                if (!ok && lane == 0) flag[0] = 1;
+                singular = singular || !ok;                   // a failed pivot poisons the rest with NaNs; nobody branches on it
                 const long long tb0 = KCLK();
                 named_bar_sync(1, NT);                        // -inv(L_KK) published; the workers' stage K-1 is complete
                 const long long tb1 = KCLK();
                 t_bar += tb1 - tb0;
-                if (flag[0]) { singular = true; break; }
                 const double2 w = Wt2[(K & 1) * 32 + lane];
                 const int rb = ltile(K + 1, 0);
                 double2 l;
@@ -498,7 +497,6 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
                 named_bar_sync(1, NT);
                 const long long tb1 = KCLK();
                 t_bar += tb1 - tb0;
-                if (flag[0]) break;
                 if (c <= NB) {
                     const double2 negW = Wt2[(K & 1) * 32 + lane];
                     double2 lk1;

@@ -50,7 +50,7 @@ constexpr int KED_HDR = 8 + KED_TABN + 2 * 128;         // doubles: flag + mbarr
 __global__ void __launch_bounds__(256) hgather_kernel(StnTable st, int q0, int nq, int k1, const int32_t* idx,
                                                       const int32_t* nn, int32_t* status, double* hc,
                                                       size_t hc_stride, int single_mth, int nbcap, const double* vario,
-                                                      int vario_is_override, int off_cp) {
+                                                      int vario_is_override, int off_cp, int nbcap_pt) {
     __shared__ int sidx[256];
     const int q = q0 + blockIdx.x;
     if (status[q] != TWXI_ST_OK) return;
@@ -77,7 +77,10 @@ __global__ void __launch_bounds__(256) hgather_kernel(StnTable st, int q0, int n
     }
     for (int I = 0; I < NB; ++I) {
         const int cnt = (I + 1) * 64;
-        double* row = out + (size_t)htile(I, 0) * 64;
+        // staged layout of a point: the strict lower triangle of tiles row by row (exactly the layout of the solve's shared
+        // L tiles, so that one bulk copy brings in a whole system), then the diagonal tiles, then the covariance parameters
+        double* row = out + (size_t)ltile(I, 0) * 64;
+        double* diag = out + (off_cp - nbcap_pt * 64) + (size_t)I * 64;
         for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
             const int i = 8 * I + ((e >> 3) & 7), j = 8 * (e >> 6) + (e & 7);
             double h = 0.0;
@@ -88,7 +91,7 @@ __global__ void __launch_bounds__(256) hgather_kernel(StnTable st, int q0, int n
                 // evaluation of the solve then needs no h == 0 case
                 if (h == 0.0) atomicCAS(status + q, TWXI_ST_OK, TWXI_ST_SINGULAR);
             }
-            row[e] = h;
+            if (e < I * 64) row[e] = h; else diag[e & 63] = h;
         }
     }
 }
@@ -170,9 +173,10 @@ struct Prob {
     double2* tl2;          // lane's fragment pointer into the shared L / N tiles: tile t is tl2[t * 32]
     double2* Nd2;          // lane's fragment of the two N_diag buffers: Nd2[(c & 1) * 32]
     const double2* hc2;    // lane's fragment pointer into the compact distance tiles of this point (global)
-    const double* tab32;
+    uint32_t tab32;        // shared address of the 2^(j/T) table
     CovPar cp;
     int NB, n, r8, q4;
+    uint32_t tb;           // lane's shared-window address of tile 0 (= tl2); -2048 / -1024: the -inv(L_KK) / N_diag buffers
 };
 
 // -V(c,c) of a diagonal tile from its raw distances (zero for the S tile c == NB)
@@ -187,19 +191,32 @@ __device__ __forceinline__ double2 neg_cov_diag(const Prob& p, int c, double2 hd
 // and, by the owner of row K+2 (u == 0), the next-but-one pivot tile
 //   N_diag(K+2) = -V(K+2,K+2) + sum_{J<=K} L(K+2,J) L(K+2,J)'.
 // Every tile of the strict lower triangle is read and written exactly twice (update, then solve).
+// Byte offset of tile row I inside the shared L / N tiles (ltile(I, 0) * 512).  Looked up instead of computed, and all
+// accesses of the stage loop go through explicit 32-bit shared addresses (lane base `tb` + row offset + immediate): the
+// compiler otherwise rebuilds the lane's generic address (S2R / S2UR / shifts) and the triangular index for every block of
+// the loop - ~40 of the ~110 instructions a worker issued per stage.
+__constant__ uint32_t c_ked_rowoff[36] = {0, 0, 512, 1536, 3072, 5120, 7680, 10752, 14336, 18432, 23040, 28160, 33792, 39936, 46592, 53760, 61440, 69632, 78336, 87552, 97280, 107520, 118272, 129536, 141312, 153600, 166400, 179712, 193536, 207872, 222720, 238080, 253952, 270336, 287232, 304640};
+__device__ __forceinline__ double2 lds2(uint32_t addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts2(uint32_t addr, const double2 v) {
+    asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
+}
+
 template <int NW>
 __device__ __forceinline__ void stage_rows(const Prob& p, int K, int u, const double2 negW, const double2 lk1, double2 vd) {
-    double2* tl2 = p.tl2;
-    const double2* pB = tl2 + ltile(K + 1, 0) * 32;           // row K+1: L(K+1, J), J < K
+    const uint32_t tb = p.tb;
+    const uint32_t pB = tb + c_ked_rowoff[K + 1];             // row K+1: L(K+1, J), J < K
+    const uint32_t ko = (uint32_t)K * 512u;
     const int c = K + 2;
     int I = c + u;
     double2 lfirst = make_double2(0.0, 0.0);                  // L(K+2,K) of the u == 0 worker
     for (; TWXI_KED_PAIR && I + NW <= p.NB; I += 2 * NW) {
-        const int r1 = ltile(I, 0) * 32, r2 = ltile(I + NW, 0) * 32;
-        const double2* pA1 = tl2 + r1;
-        const double2* pA2 = tl2 + r2;
-        const double2 n1 = pA1[K * 32], n2 = pA2[K * 32];
-        double2 acc1 = pA1[K * 32 + 32], acc2 = pA2[K * 32 + 32];
+        const uint32_t pA1 = tb + c_ked_rowoff[I], pA2 = tb + c_ked_rowoff[I + NW];
+        const double2 n1 = lds2(pA1 + ko), n2 = lds2(pA2 + ko);
+        double2 acc1 = lds2(pA1 + ko + 512u), acc2 = lds2(pA2 + ko + 512u);
         double2 l1, l2;
         dmma_z(l1, n1.x, negW.x); dmma_z(l2, n2.x, negW.x);
         dmma(l1, n1.y, negW.y); dmma(l2, n2.y, negW.y);
@@ -207,58 +224,60 @@ __device__ __forceinline__ void stage_rows(const Prob& p, int K, int u, const do
         dmma_z(e1, l1.x, lk1.x); dmma_z(e2, l2.x, lk1.x);
         dmma(e1, l1.y, lk1.y); dmma(e2, l2.y, lk1.y);
         int J = 0;
-        for (; J + 1 < K; J += 2) {
-            const double2 b0 = pB[J * 32], b1 = pB[J * 32 + 32];
-            const double2 a10 = pA1[J * 32], a11 = pA1[J * 32 + 32];
-            const double2 a20 = pA2[J * 32], a21 = pA2[J * 32 + 32];
+        uint32_t jo = 0;
+        for (; J + 1 < K; J += 2, jo += 1024u) {
+            const double2 b0 = lds2(pB + jo), b1 = lds2(pB + jo + 512u);
+            const double2 a10 = lds2(pA1 + jo), a11 = lds2(pA1 + jo + 512u);
+            const double2 a20 = lds2(pA2 + jo), a21 = lds2(pA2 + jo + 512u);
             dmma(acc1, a10.x, b0.x); dmma(acc2, a20.x, b0.x); dmma(e1, a11.x, b1.x); dmma(e2, a21.x, b1.x);
             dmma(acc1, a10.y, b0.y); dmma(acc2, a20.y, b0.y); dmma(e1, a11.y, b1.y); dmma(e2, a21.y, b1.y);
         }
         if (J < K) {
-            const double2 b0 = pB[J * 32], a10 = pA1[J * 32], a20 = pA2[J * 32];
+            const double2 b0 = lds2(pB + jo), a10 = lds2(pA1 + jo), a20 = lds2(pA2 + jo);
             dmma(acc1, a10.x, b0.x); dmma(acc2, a20.x, b0.x);
             dmma(acc1, a10.y, b0.y); dmma(acc2, a20.y, b0.y);
         }
-        tl2[r1 + K * 32] = l1; tl2[r2 + K * 32] = l2;
+        sts2(pA1 + ko, l1); sts2(pA2 + ko, l2);
         acc1.x += e1.x; acc1.y += e1.y; acc2.x += e2.x; acc2.y += e2.y;
-        tl2[r1 + K * 32 + 32] = acc1; tl2[r2 + K * 32 + 32] = acc2;
+        sts2(pA1 + ko + 512u, acc1); sts2(pA2 + ko + 512u, acc2);
         if (I == c) lfirst = l1;
     }
     for (; I <= p.NB; I += NW) {
-        const int r1 = ltile(I, 0) * 32;
-        const double2* pA1 = tl2 + r1;
-        const double2 n1 = pA1[K * 32];
+        const uint32_t pA1 = tb + c_ked_rowoff[I];
+        const double2 n1 = lds2(pA1 + ko);
         double2 acc1 = make_double2(0.0, 0.0);
-        if (I > K + 1) acc1 = pA1[K * 32 + 32];
+        if (I > K + 1) acc1 = lds2(pA1 + ko + 512u);
         double2 l1;
         dmma2_z(l1, n1, negW);
         double2 e1;
         dmma2_z(e1, l1, lk1);
         int J = 0;
-        for (; J + 1 < K; J += 2) {
-            const double2 b0 = pB[J * 32], a0 = pA1[J * 32], b1 = pB[J * 32 + 32], a1 = pA1[J * 32 + 32];
+        uint32_t jo = 0;
+        for (; J + 1 < K; J += 2, jo += 1024u) {
+            const double2 b0 = lds2(pB + jo), a0 = lds2(pA1 + jo), b1 = lds2(pB + jo + 512u), a1 = lds2(pA1 + jo + 512u);
             dmma(acc1, a0.x, b0.x); dmma(e1, a1.x, b1.x);
             dmma(acc1, a0.y, b0.y); dmma(e1, a1.y, b1.y);
         }
-        if (J < K) dmma2(acc1, pA1[J * 32], pB[J * 32]);
-        tl2[r1 + K * 32] = l1;
+        if (J < K) dmma2(acc1, lds2(pA1 + jo), lds2(pB + jo));
+        sts2(pA1 + ko, l1);
         acc1.x += e1.x; acc1.y += e1.y;
-        tl2[r1 + K * 32 + 32] = acc1;
+        sts2(pA1 + ko + 512u, acc1);
         if (I == c) lfirst = l1;
     }
     if (u == 0 && c <= p.NB) {                                // pivot tile of stage K+2 (the S tile for c == NB)
-        const double2* pA = tl2 + ltile(c, 0) * 32;
+        const uint32_t pA = tb + c_ked_rowoff[c];
         double2 acc = vd, e;
         dmma2_z(e, lfirst, lfirst);
         int J = 0;
-        for (; J + 1 < K; J += 2) {
-            const double2 a0 = pA[J * 32], a1 = pA[J * 32 + 32];
+        uint32_t jo = 0;
+        for (; J + 1 < K; J += 2, jo += 1024u) {
+            const double2 a0 = lds2(pA + jo), a1 = lds2(pA + jo + 512u);
             dmma(acc, a0.x, a0.x); dmma(e, a1.x, a1.x);
             dmma(acc, a0.y, a0.y); dmma(e, a1.y, a1.y);
         }
-        if (J < K) { const double2 a0 = pA[J * 32]; dmma2(acc, a0, a0); }
+        if (J < K) { const double2 a0 = lds2(pA + jo); dmma2(acc, a0, a0); }
         acc.x += e.x; acc.y += e.y;
-        p.Nd2[(c & 1) * 32] = acc;
+        sts2(tb - 1024u + (uint32_t)(c & 1) * 512u, acc);     // N_diag buffer c & 1 (two tiles in front of the L tiles)
     }
 }
 
@@ -277,7 +296,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
     int* flag = reinterpret_cast<int*>(sm);                   // (profiling builds only)
     (void)flag;
     void* mbar = sm + 2;                                      // mbarrier of the distance-tile bulk copies
-    double* tab32 = sm + 8;                                   // KED_TABN: 2^(j/KED_TABN)
+    double* tabp = sm + 8;                                    // KED_TABN: 2^(j/KED_TABN)
     double2* Wt2 = reinterpret_cast<double2*>(sm + 8 + KED_TABN);          // 2 x 64: -inv(L_KK), double-buffered by K & 1
     double2* Nd2 = reinterpret_cast<double2*>(sm + 8 + KED_TABN + 128);    // 2 x 64: N_diag of column c, double-buffered by c & 1
     double* tiles = sm + KED_HDR;
@@ -290,7 +309,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
     const int NB = a.nbv;
     const int count = a.bcount[NB], start = a.bstart[NB];
     const int N = a.st.n;
-    for (int i = tid; i < KED_TABN; i += NT) tab32[i] = exp2((double)i / KED_TABN);
+    for (int i = tid; i < KED_TABN; i += NT) tabp[i] = exp2((double)i / KED_TABN);
     if (tid == 0) mbar_init(mbar, 1);
     uint32_t parity = 0;
     const long long lane_zero = (long long)(lane * a.zero);
@@ -298,8 +317,13 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
     Prob p;
     p.tl2 = reinterpret_cast<double2*>(tiles) + lane;
     p.Nd2 = Nd2 + lane;
+    const uint32_t tab32 = __shfl_sync(0xffffffffu, smem_u32(tabp), lane);    // (kept in a register, like p.tb below)
     p.tab32 = tab32;
     p.NB = NB; p.r8 = lane >> 2; p.q4 = lane & 3;
+    // (passed through a shuffle so that the compiler keeps the address in a register instead of rebuilding it from the
+    // thread and CTA ids at every use)
+    p.tb = __shfl_sync(0xffffffffu, smem_u32(tiles) + (uint32_t)lane * 16u, lane);
+    static_assert(KED_HDR == 8 + KED_TABN + 256, "stage_rows addresses the N_diag / W buffers relative to the tiles");
     double2* const tl2 = p.tl2;
     const uint32_t tx_bytes = (uint32_t)(NB * (NB - 1) / 2) * 512u;     // tile rows 1..NB-1, I tiles each
 
@@ -334,8 +358,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
             if (tx_bytes) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_expect_tx(mbar, tx_bytes);
-                for (int I = 1; I < NB; ++I)
-                    bulk_g2s(tiles + ltile(I, 0) * 64, hc + htile(I, 0) * 64, (uint32_t)I * 512u, mbar);
+                bulk_g2s(tiles, hc, tx_bytes, mbar);           // tile rows 1..NB-1: same layout in global and shared memory
             }
         }
         // ---- augmented rows -B' = -[1, dlon, dlat, delev, dlst, y - yref, c0]' into tile row NB: one station per
@@ -360,10 +383,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
         // raw distances of the diagonal tiles 0, 1 (-> N_diag buffers) and 2 (first look-ahead column)
         double2 hd = make_double2(0.0, 0.0), hd1 = make_double2(0.0, 0.0);
         if (warp == NW) {                                     // the diagonal warp owns V(0,0) and V(1,1)
-            hd = p.hc2[0];
-            if (NB > 1) hd1 = p.hc2[htile(1, 1) * 32];
+            hd = p.hc2[a.off_diag / 2];
+            if (NB > 1) hd1 = p.hc2[a.off_diag / 2 + 32];
         }
-        if (warp == NW - 1 && NB > 2) hd = p.hc2[htile(2, 2) * 32];     // look-ahead worker (u == 0)
+        if (warp == NW - 1 && NB > 2) hd = p.hc2[a.off_diag / 2 + 2 * 32];     // look-ahead worker (u == 0)
         p.cp.c00 = cp0.x; p.cp.nk = cp0.y; p.cp.c0 = cp1.x; p.cp.c1 = cp1.y;
         p.cp.c2 = cp2.x; p.cp.c3 = cp2.y; p.cp.c4 = cp3.x;
         // The parameters are warp-uniform and end up in uniform registers; an FP64 instruction takes one uniform / immediate
@@ -412,20 +435,24 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
             const int T0 = NB >= 2 ? ltile(NB - 1, 0) : 0;
             constexpr int NWT = NW + 1;
             int t = warp;
+            const uint32_t tb = p.tb;
             for (; t + 3 * NWT < T0; t += 4 * NWT) {
-                const double2 h1 = tl2[t * 32], h2 = tl2[(t + NWT) * 32], h3 = tl2[(t + 2 * NWT) * 32], h4 = tl2[(t + 3 * NWT) * 32];
+                const uint32_t at = tb + (uint32_t)t * 512u;
+                const double2 h1 = lds2(at), h2 = lds2(at + NWT * 512u), h3 = lds2(at + 2 * NWT * 512u), h4 = lds2(at + 3 * NWT * 512u);
                 double2 v1, v2, v3, v4;
                 v1.x = ncov_pos(h1.x, p.cp, tab32); v2.x = ncov_pos(h2.x, p.cp, tab32); v3.x = ncov_pos(h3.x, p.cp, tab32); v4.x = ncov_pos(h4.x, p.cp, tab32);
                 v1.y = ncov_pos(h1.y, p.cp, tab32); v2.y = ncov_pos(h2.y, p.cp, tab32); v3.y = ncov_pos(h3.y, p.cp, tab32); v4.y = ncov_pos(h4.y, p.cp, tab32);
-                tl2[t * 32] = v1; tl2[(t + NWT) * 32] = v2; tl2[(t + 2 * NWT) * 32] = v3; tl2[(t + 3 * NWT) * 32] = v4;
+                sts2(at, v1); sts2(at + NWT * 512u, v2); sts2(at + 2 * NWT * 512u, v3); sts2(at + 3 * NWT * 512u, v4);
             }
             for (; t < T0; t += NWT) {
-                const double2 h1 = tl2[t * 32];
-                tl2[t * 32] = make_double2(ncov_pos(h1.x, p.cp, tab32), ncov_pos(h1.y, p.cp, tab32));
+                const uint32_t at = tb + (uint32_t)t * 512u;
+                const double2 h1 = lds2(at);
+                sts2(at, make_double2(ncov_pos(h1.x, p.cp, tab32), ncov_pos(h1.y, p.cp, tab32)));
             }
             const bool plain = 8 * NB <= n;                   // last row of V: identity padding beyond n
             for (int c = warp; c < NB - 1; c += NW + 1) {
-                tl2[(T0 + c) * 32] = ncov_tile(tl2[(T0 + c) * 32], 8 * (NB - 1) + p.r8, 8 * c + 2 * p.q4, n, p.cp, tab32, plain);
+                const uint32_t at = tb + (uint32_t)(T0 + c) * 512u;
+                sts2(at, ncov_tile(lds2(at), 8 * (NB - 1) + p.r8, 8 * c + 2 * p.q4, n, p.cp, tab32, plain));
             }
             if (warp == NW) {
                 p.Nd2[0] = neg_cov_diag(p, 0, hd);
@@ -464,11 +491,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
                 named_bar_sync(1, NT);                        // -inv(L_KK) published; the workers' stage K-1 is complete
                 const long long tb1 = KCLK();
                 t_bar += tb1 - tb0;
-                const double2 w = Wt2[(K & 1) * 32 + lane];
-                const int rb = ltile(K + 1, 0);
+                const double2 w = lds2(p.tb - 2048u + (uint32_t)(K & 1) * 512u);
                 double2 l;
-                dmma2_z(l, tl2[(rb + K) * 32], w);            // L(K+1,K) = N(K+1,K) (-W)'
-                double2 nd = Nd2[((K + 1) & 1) * 32 + lane];  // -V + sum_{J<K} L(K+1,J) L(K+1,J)'
+                dmma2_z(l, lds2(p.tb + c_ked_rowoff[K + 1] + (uint32_t)K * 512u), w);    // L(K+1,K) = N(K+1,K) (-W)'
+                double2 nd = lds2(p.tb - 1024u + (uint32_t)((K + 1) & 1) * 512u);        // -V + sum_{J<K} L(K+1,J) L(K+1,J)'
                 dmma2(nd, l, l);
                 D.x = -nd.x; D.y = -nd.y;                     // D_{K+1}; for K+1 == NB this is -S
 #ifdef TWXI_KED_PROFILE
@@ -491,16 +517,16 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) ked_kernel(KedArgs a) {
                 double2 vd = make_double2(0.0, 0.0);
                 if (u == 0) {                                 // -V(c,c) before the barrier, next diagonal tile after it
                     vd = neg_cov_diag(p, c, hd);
-                    if (c + 1 < NB) hd = p.hc2[htile(c + 1, c + 1) * 32];
+                    if (c + 1 < NB) hd = p.hc2[a.off_diag / 2 + (c + 1) * 32];
                 }
                 const long long tb0 = KCLK();
                 named_bar_sync(1, NT);
                 const long long tb1 = KCLK();
                 t_bar += tb1 - tb0;
                 if (c <= NB) {
-                    const double2 negW = Wt2[(K & 1) * 32 + lane];
+                    const double2 negW = lds2(p.tb - 2048u + (uint32_t)(K & 1) * 512u);
                     double2 lk1;
-                    dmma2_z(lk1, tl2[(ltile(K + 1, 0) + K) * 32], negW);   // L(K+1,K), recomputed by every worker
+                    dmma2_z(lk1, lds2(p.tb + c_ked_rowoff[K + 1] + (uint32_t)K * 512u), negW);   // L(K+1,K), recomputed by every worker
                     stage_rows<NW>(p, K, u, negW, lk1, vd);
                     t_x += KCLK() - tb1;
                 }
@@ -643,6 +669,7 @@ int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
     a.st = c.st; a.npts = b.npts; a.k1 = b.k1;
     a.idx = b.idx; a.h0 = b.h0; a.nn = b.nn;
     a.off_cp = off_cp;
+    a.off_diag = off_cp - nbmax * 64;
     a.qlon = b.lon; a.qlat = b.lat; a.qelev = b.elev; a.qlst = b.lst;
     a.hc = w.hc; a.hc_stride = hc_stride; a.list = w.list; a.bstart = bstart; a.bcount = bcount;
     a.mean = b.mean; a.var = b.var; a.status = b.status;
@@ -653,7 +680,7 @@ int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
         const int nq = std::min(qcap, b.npts - q0);
         a.q0 = q0;
         hgather_kernel<<<nq, 256, 0, c.stream>>>(c.st, q0, nq, b.k1, b.idx, b.nn, b.status, w.hc, hc_stride, mth >= 1 ? mth - 1 : -1, nbmax,
-                                                      vario_override ? vario_override : b.vario, vario_override != nullptr, off_cp);
+                                                      vario_override ? vario_override : b.vario, vario_override != nullptr, off_cp, nbmax);
         TWXI_LAUNCH_CHECK();
         const int nt = nq * 12, nblk = (nt + 255) / 256;
         ked_bin_kernel<<<nblk, 256, 0, c.stream>>>(q0, nq, single, b.nn, b.status, w.blockcnt);

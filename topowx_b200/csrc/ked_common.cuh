@@ -19,6 +19,7 @@ struct KedArgs {
     const int32_t* idx;
     const double* h0;
     const int32_t* nn;
+    int off_diag;              // offset (doubles) of the diagonal distance tiles inside a point's staged block
     int off_cp;                // offset (doubles) of the 12 x 8 covariance parameters inside a point's staged block
     const double* qlon;
     const double* qlat;
@@ -40,8 +41,6 @@ struct KedArgs {
 
 // shared-memory L tiles: rows 1..NBv, row I holds tiles J = 0..I-1 (diagonal tiles are never stored)
 __device__ __forceinline__ int ltile(int I, int J) { return I * (I - 1) / 2 + J; }
-// compact distance tiles: rows 0..NB-1, row I holds tiles J = 0..I
-__device__ __forceinline__ int htile(int I, int J) { return I * (I + 1) / 2 + J; }
 
 
 // ---- covariances, barrier / bulk-copy helpers, the 5x5 GLS --------------------------------------------------------
@@ -79,7 +78,7 @@ __device__ __forceinline__ void covpar_set(CovPar& cp, double nug, double psill,
     cp.c4 = ps * (a * a * a * a * (1.0 / 24.0)); cp.c5 = ps * (a * a * a * a * a * (1.0 / 120.0));
 }
 // -C(h) for h > 0 (also minus the value the exponential model takes at h == 0, without the nugget)
-__device__ __forceinline__ double ncov_pos(double h, const CovPar& cp, const double* __restrict__ tab) {
+__device__ __forceinline__ double ncov_pos(double h, const CovPar& cp, uint32_t tab) {
 #if TWXI_KED_FAKE == 2
     return cp.c0 * (h * cp.nk);
 #else
@@ -95,18 +94,20 @@ __device__ __forceinline__ double ncov_pos(double h, const CovPar& cp, const dou
     p = fma(f, p, cp.c1);
     p = fma(f, p, cp.c0);
     ki = max(ki, -KED_TABN * 1000);                           // below 2^-1000 the value does not matter, the exponent must stay valid
-    const double v = p * tab[ki & (KED_TABN - 1)];
-    return __hiloint2double(__double2hiint(v) + ((ki >> KED_TABLOG) << 20), __double2loint(v));
+    double t;                                                 // tab[k mod T] (tab: 32-bit shared address of the table)
+    asm("ld.shared.f64 %0, [%1];" : "=d"(t) : "r"(tab + (uint32_t)(ki & (KED_TABN - 1)) * 8u));
+    // 2^(k div T) goes into the exponent of the table value
+    return p * __hiloint2double(__double2hiint(t) + ((ki >> KED_TABLOG) << 20), __double2loint(t));
 #endif
 }
 // -C(h) of a pair that may be co-located (point - station): -(nug+psill) at h == 0
-__device__ __forceinline__ double ncov(double h, const CovPar& cp, const double* tab) {
+__device__ __forceinline__ double ncov(double h, const CovPar& cp, uint32_t tab) {
     const double e = ncov_pos(h, cp, tab);
     return h == 0.0 ? -cp.c00 : e;
 }
 // -V tile (I, K) from its distance tile in C-fragment layout; lane holds (i, j) and (i, j+1).
 // `plain` (warp-uniform): the tile is strictly below the diagonal and inside the n x n block, so no masking.
-__device__ __forceinline__ double2 ncov_tile(double2 h, int i, int j, int n, const CovPar& cp, const double* tab32,
+__device__ __forceinline__ double2 ncov_tile(double2 h, int i, int j, int n, const CovPar& cp, uint32_t tab32,
                                              bool plain) {
     double2 v;                                                // (co-located station pairs never get here: hgather)
     v.x = ncov_pos(h.x, cp, tab32);

@@ -245,8 +245,7 @@ __device__ __forceinline__ void stage_rows(const Prob& p, int K, int u, const do
     for (; I <= p.NB; I += NW) {
         const uint32_t pA1 = tb + c_ked_rowoff[I];
         const double2 n1 = lds2(pA1 + ko);
-        double2 acc1 = make_double2(0.0, 0.0);
-        if (I > K + 1) acc1 = lds2(pA1 + ko + 512u);
+        double2 acc1 = lds2(pA1 + ko + 512u);                 // (I >= K + 2: the tile exists)
         double2 l1;
         dmma2_z(l1, n1, negW);
         double2 e1;

@@ -12,9 +12,10 @@
 //
 // Kernels.
 //  1. hgather: per point, the station-station distances of its nmax = max_m k_norm nearest stations are
-//     gathered ONCE from the N x N table into a compact buffer of row-major 8x8 tiles (lower block triangle,
-//     neighbours in distance-rank order so every month's set is a leading block).  The 12 monthly systems then
-//     stream their tiles with bulk copies instead of re-gathering 32-byte sectors per pair.
+//     gathered ONCE from the N x N table into a compact buffer of row-major 8x8 tiles (strict lower block triangle
+//     row by row - the layout of the solve's shared L tiles - then the diagonal tiles, then the covariance parameters
+//     of the 12 months; neighbours in distance-rank order so every month's set is a leading block).  The 12 monthly
+//     systems then stream their tiles with one bulk copy each instead of re-gathering 32-byte sectors per pair.
 //  2. bin/scan/scatter: (point, month) problems are counting-sorted by NB = ceil(n/8) so that each size class
 //     is launched with exactly the shared memory it needs (occupancy 6 CTAs/SM at n ~ 80, 2 at n = 147).
 //  3. ked: persistent CTAs, one problem at a time per CTA, problems strided statically over the CTAs of the size
@@ -24,11 +25,11 @@
 //     operand and as the transposed B operand of two mma.sync.m8n8k4.f64 ("DMMA") steps, so X*Y' is two DMMAs and
 //     tiles never need re-layout.  Tile row NB holds B' (7 rows); its diagonal tile ends up as S.
 //     Data flow per problem (N := sum L L' - V, the negated Schur complement, so DMMAs accumulate in place):
-//       prologue   one thread issues a TMA bulk copy (cp.async.bulk + mbarrier) per tile row that lands the raw
-//                  distance tiles straight in the shared-memory slots of L; meanwhile all warps build B'; then one
+//       prologue   one thread issues ONE TMA bulk copy (cp.async.bulk + mbarrier) that lands the raw distance
+//                  tiles straight in the shared-memory slots of L; meanwhile all warps build B'; then one
 //                  pass turns every slot into -C(h) (ked_common.cuh: ncov_pos).
-//       stage K    diagonal warp: -W = -inv(chol(D_K))' (chol8_inverse_t: fraction-free elimination of the pivot tile
-//                  as DMMA outer products), publish it; ONE CTA barrier; then it forms L(K+1,K) and D_{K+1} itself
+//       stage K    diagonal warp: -W = -inv(chol(D_K))' (chol8_inverse_ldl: LDL' elimination of the pivot tile with
+//                  DMMA outer products for the tile and for the inverse), publish it; ONE CTA barrier; then it forms L(K+1,K) and D_{K+1} itself
 //                  and goes on factoring while the workers are busy with stage K.
 //                  workers (rows dealt round-robin per stage, two rows per pass = four independent DMMA chains):
 //                  L(I,K) = N(I,K)(-W)';  N(I,K+1) += sum_{J<=K} L(I,J) L(K+1,J)' (column K+1 is final after the

@@ -618,7 +618,7 @@ int launch_krig(Ctx& c, Batch& b, int mth, const double* vario_override) {
             TWXI_CUDA(cudaFuncSetAttribute(KED_VARIANTS[v].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         // default choice per size class (measured on B200, profiles/ked_variants_r01.txt); TWXI_KED_VAR overrides it with
         // one digit (variant index) per size class NB = 1, 2, ...
-        static const char* dflt = "000000002334445555555";      // re-checked on the C5 tiles in round 2 (profiles/kedvar_c5_r02_j.log)
+        static const char* dflt = "000000002233445555555";      // re-checked on the C5 tiles in round 2 (profiles/kedvar_c5_r02_j.log, _l.log)
         const char* sel = getenv("TWXI_KED_VAR");
         if (!sel || (int)strlen(sel) < KED_NBMAX) sel = dflt;
         for (int nb = 1; nb <= KED_NBMAX; ++nb) {

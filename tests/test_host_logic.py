@@ -261,3 +261,18 @@ def test_predictor_grids_lookup(tmp_path):
     pt[db.LON] = lon_c + 10.0
     with pytest.raises(Exception):
         pg.setPtValues(pt)
+
+
+def test_ked_row_offset_table_matches_the_tile_indexing():
+    """csrc/ked.cu looks the byte offset of tile row I up in c_ked_rowoff instead of computing ltile(I, 0) * 512; the table
+    must cover every row the largest size class can touch (rows 0 .. KED_NBMAX, the last one being the augmented B' row)."""
+    import os, re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "topowx_b200", "csrc", "ked.cu")).read()
+    m = re.search(r"c_ked_rowoff\[(\d+)\]\s*=\s*\{([^}]*)\}", src)
+    vals = [int(v) for v in m.group(2).split(",")]
+    assert len(vals) == int(m.group(1))
+    assert vals == [i * (i - 1) // 2 * 512 for i in range(len(vals))]
+    hdr = open(os.path.join(root, "include", "twxi.h")).read()
+    max_n = int(re.search(r"#define\s+TWXI_MAX_KRIG_NNGHS\s+(\d+)", hdr).group(1))
+    assert len(vals) > max_n // 8 + 1
